@@ -1,0 +1,122 @@
+/* sdfnet.h -- C ABI of the B200-native neural-SDF hot path.
+ *
+ * One shared library (libsdfnet.so, built from sdf-representation_b200/csrc by __graft_entry__.build()),
+ * extern "C", plain pointers and sizes, no torch types, no exceptions across the boundary.  All data pointers are
+ * DEVICE pointers owned by the caller (PyTorch); the library owns only its packed-weight cache and gradient
+ * accumulators.  Every entry point returns 0 on success and a non-zero code otherwise; sdfnet_last_error() then
+ * describes the failure.  Calls are asynchronous on the CUDA stream passed in (a cudaStream_t cast to void*).
+ * There is no CPU fallback.
+ *
+ * Each entry point names the reference (newton-raphson/sdf-representation) interface it replaces.
+ */
+#ifndef SDFNET_H_
+#define SDFNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Network description == the constructor arguments of model/networks.py:29-38 ImplicitNet(d_in, dims, skip_in,
+ * beta, ...) restricted to what the kernels support: d_in = 3, all hidden widths equal (multiple of 64, <= 512),
+ * at most one skip layer.  beta > 0 selects Softplus(beta); beta == 0 selects ReLU with tanh on the output
+ * (model/networks.py:79-83,104-105). */
+typedef struct sdfnet_desc {
+  int32_t d_in;
+  int32_t hidden;       /* H */
+  int32_t num_hidden;   /* number of hidden layers L; the net has L+1 Linear layers lin0..linL */
+  int32_t skip_layer;   /* index in skip_in (layer whose input is cat([x, input])/sqrt(2)); 0 = none */
+  float beta;
+  int32_t dtype;        /* 16-bit operand type of the tensor-core GEMMs: 0 = bf16, 1 = fp16 */
+  int32_t precision;    /* 0 = single pass ("fast"), 1 = hi/lo split operands ("parity", fp32-grade) */
+  int32_t device;       /* CUDA device ordinal */
+} sdfnet_desc;
+
+typedef struct sdfnet_handle* sdfnet_t;
+
+/* IGRLOSS hyper-parameters: model/losses.py:100-105 (+ the data-term variant). */
+typedef struct sdfnet_igr_cfg {
+  float delta, tau, lambda_g, regularizer_threshold;
+  int32_t data_term;    /* 0 = "pairwise": mean over the reference's (N,1)-(N,) broadcast; 1 = "pointwise" */
+  float mean_t;         /* pairwise: global mean of clamp(S, +-delta) over the whole (multi-GPU) batch */
+  int64_t n_global;     /* loss normaliser: points in the whole batch across ranks */
+  const float* mean_t_dev; /* optional DEVICE pointer to mean_t (overrides mean_t; avoids a host sync per step) */
+} sdfnet_igr_cfg;
+
+const char* sdfnet_last_error(void);
+
+/* model/networks.py:29-83 (construction); the packed copy replaces nn.Linear's own weight storage on the hot path */
+int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out);
+int sdfnet_destroy(sdfnet_t h);
+
+/* Re-pack lin{i}.weight / lin{i}.bias (fp32 device pointers, layouts [out,in] and [out], i = 0..L) into UMMA
+ * operand images.  Call after every optimizer step (executor/executor.py:177). */
+int sdfnet_pack_weights(sdfnet_t h, const float* const* weights, const float* const* biases, void* stream);
+
+/* Bytes of scratch one point tile set needs, so callers can size `ws`: mode 0 = forward_grad, 1 = training. */
+size_t sdfnet_workspace_bytes(sdfnet_t h, int64_t n_points, int32_t mode);
+
+/* model/networks.py:87-106 ImplicitNet.forward: x [n,3] -> sdf [n] */
+int sdfnet_forward(sdfnet_t h, const float* x, int64_t n, float* sdf_out, void* stream);
+
+/* model/losses.py:283-296 compute_normal / executor/executordistributed.py:10-19 gradient /
+ * ops/conversion_test/test_loading.cpp:62,99: sdf [n] and grad_x sdf [n,3] */
+int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float* sdf_out, float* grad_out, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* executor/executor.py:351-383 and evaluations/post_process.py:46-53,83-88: SDF on the points
+ * [first, first+count) of the flattened n_axis^3 'ij' meshgrid (x slowest), coordinates taken from `axis`
+ * (= torch.linspace(-1, 1, n_axis) evaluated by the caller). */
+int sdfnet_grid_eval(sdfnet_t h, const float* axis, int32_t n_axis, int64_t first, int64_t count, float* sdf_out,
+                     void* stream);
+
+/* evaluations/compare_octree_dl.py:20-36 (per-node query), batched per level: SDF at the centres of the cells
+ * `keys` (3 x level-bit Morton codes, x bit highest) of the octree over [-1,1]^3; refine_flags[i] = 1 iff
+ * |sdf| <= band * h_level (h_level = 2 / 2^level), the single-rounding fp32 predicate of oracle/octree.py. */
+int sdfnet_octree_level(sdfnet_t h, const uint64_t* keys, int64_t count, int32_t level, float band, float* sdf_out,
+                        uint8_t* refine_flags, void* stream);
+
+/* Generic backward of the network (autograd path of model/losses.py:283-296 + loss.backward()):
+ * given per-point seeds fbar = dL/df [n] (may be NULL) and gbar = dL/d(grad_x f) [n,3] (may be NULL), ACCUMULATE
+ * dL/d(parameters) into the library's fp32 accumulators.  Fetch with sdfnet_read_grads. */
+int sdfnet_backward(sdfnet_t h, const float* x, int64_t n, const float* fbar, const float* gbar, void* ws,
+                    size_t ws_bytes, void* stream);
+int sdfnet_zero_grads(sdfnet_t h, void* stream);
+/* grads: flat fp32 [num_params] in state_dict order lin0.weight, lin0.bias, lin1.weight, ... (model/networks.py:77) */
+int sdfnet_read_grads(sdfnet_t h, float* grads, float scale, void* stream);
+int64_t sdfnet_num_params(sdfnet_t h);
+
+/* model/losses.py:109-137 IGRLOSS.forward + executor/executor.py:174-176 backward, fused:
+ * x [n,3], y [n,4] = [S, nx, ny, nz].  Accumulates parameter gradients (see sdfnet_read_grads) and adds this
+ * shard's loss terms to loss_sums[8] (double, device): sum p, sum p^2, sum t, sum t^2, sum (p-t)^2, sum reg,
+ * sum eik, count. */
+int sdfnet_train_step_igr(sdfnet_t h, const float* x, const float* y, int64_t n, const sdfnet_igr_cfg* cfg,
+                          double* loss_sums, void* ws, size_t ws_bytes, void* stream);
+
+/* executor/executordistributed.py:63-79 point-cloud step: surface points x [n,3] (|f| term) and perturbed points
+ * xp [m,3] (eikonal term); loss_sums[0] += sum |f|, loss_sums[1] += sum (|g|-1)^2.  n_global / m_global are the
+ * normalisers over all ranks. */
+int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int64_t n_global, const float* xp, int64_t m,
+                          int64_t m_global, float lambda_g, double* loss_sums, void* ws, size_t ws_bytes,
+                          void* stream);
+
+/* executor/executor.py:160,177 torch.optim.Adam(lr).step() fused over the flat parameter vector. */
+int sdfnet_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* executor/executor.py:388 marching_cubes(level=0) -- cell classification only: for the (nx-1)(ny-1)(nz-1) cells
+ * of an sdf block [nx,ny,nz], case_index (8-bit corner sign mask, bit c set iff corner c < 0) and the compacted
+ * list of active cells (mask not 0 or 255). */
+int sdfnet_mc_classify(const float* sdf, int32_t nx, int32_t ny, int32_t nz, uint8_t* case_index,
+                       int64_t* active_cells, int64_t* n_active, void* stream);
+
+/* Octree refinement (build-defined): children keys of the flagged cells, in order. */
+int sdfnet_octree_refine(const uint64_t* keys, const uint8_t* flags, int64_t count, uint64_t* child_keys,
+                         int64_t* n_children, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFNET_H_ */

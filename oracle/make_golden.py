@@ -1,0 +1,163 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (``/root/reference/model/networks.py``,
+``model/losses.py``, loop bodies of ``executor/executor.py:174-176`` and ``executor/executordistributed.py:63-79``)
+on CPU in the build container.  The reference cannot travel to the GPU box, the vectors can.
+
+    python oracle/make_golden.py            # needs /root/reference
+
+Test infrastructure only.
+"""
+import contextlib
+import hashlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("SDF_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from model import losses as ref_losses  # noqa: E402
+from model import networks as ref_networks  # noqa: E402
+
+import sdf_oracle as orc  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def perturb(model, seed, scale):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1 + scale * torch.randn(p.shape, generator=g))
+            p.add_(0.02 * scale * torch.randn(p.shape, generator=g))
+
+
+def params_np(model):
+    return {k.replace(".", "_"): v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def grads_np(model, prefix):
+    out = {}
+    for k, p in model.named_parameters():
+        out[prefix + k.replace(".", "_")] = p.grad.detach().numpy().copy()
+        p.grad = None
+    return out
+
+
+def points(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 3, generator=g) * 2 - 1
+
+
+def case_softplus():
+    torch.manual_seed(7)
+    model = quiet(ref_networks.ImplicitNet, 3, [128] * 4, (2,), 100.0, True)
+    perturb(model, 11, 0.3)
+    n = 333
+    x = points(n, 1)
+    y = orc.torus_labels(x)
+    y[::17, 1:] = 0.0  # zero label normals: cosine-similarity eps path
+    d = {"skip": np.int64(2), "beta": np.float64(100.0), "hidden": np.int64(128), "num_hidden": np.int64(4), "x": x.numpy(), "y": y.numpy()}
+    d.update(params_np(model))
+    # forward + compute_normal (model/networks.py:87-106, model/losses.py:283-296)
+    f = model(x).detach()
+    g = ref_losses.compute_normal(model, x.clone()).detach()
+    d["f"], d["g"] = f.numpy()[:, 0], g.numpy()
+    # IGRLOSS step (model/losses.py:109-137 + executor/executor.py:174-176)
+    loss_fn = ref_losses.IGRLOSS(0.1, 1.0, 0.1, 1.0)
+    loss = quiet(loss_fn, x.clone(), y, model, 0)
+    loss.backward()
+    d["igr_loss"] = np.float64(loss.item())
+    d.update(grads_np(model, "igr_grad_"))
+    # WeightedSmoothL2Loss (model/losses.py:50-69)
+    loss = ref_losses.WeightedSmoothL2Loss(0.5, 0.1)(x.clone(), y, model, 0)
+    loss.backward()
+    d["wsl2_loss"] = np.float64(loss.item())
+    d.update(grads_np(model, "wsl2_grad_"))
+    # point-cloud step (executor/executordistributed.py:63-79)
+    gen = torch.Generator().manual_seed(3)
+    xp = (x[torch.randperm(n, generator=gen)[: n // 3]] + torch.randn(n // 3, 3, generator=gen) * 1e-4).clone()
+    xp.requires_grad = True
+    pred = model(x)
+    pred_s = model(xp)
+    surf = pred.abs().mean()
+    ones = torch.ones_like(pred_s)
+    grads = torch.autograd.grad(pred_s, xp, ones, create_graph=True, retain_graph=True, only_inputs=True)[0][:, -3:]
+    eik = ((grads.norm(2, dim=-1) - 1) ** 2).mean()
+    loss = surf + 0.1 * eik
+    loss.backward()
+    d["xp"] = xp.detach().numpy()
+    d["pcd_loss"] = np.float64(loss.item())
+    d["pcd_terms"] = np.array([surf.item(), eik.item()])
+    d.update(grads_np(model, "pcd_grad_"))
+    np.savez_compressed(os.path.join(OUT, "softplus_skip_128x4.npz"), **d)
+
+
+def case_relu():
+    # the shipped ini's model family: skip_connection = 0 => ReLU + tanh, geometric_init False (tests/test_config.ini)
+    torch.manual_seed(5)
+    model = quiet(ref_networks.ImplicitNet, 3, [128] * 3, (), 0, False)
+    n = 257
+    x = points(n, 2)
+    y = orc.torus_labels(x)
+    d = {"skip": np.int64(0), "beta": np.float64(0.0), "hidden": np.int64(128), "num_hidden": np.int64(3), "x": x.numpy(), "y": y.numpy()}
+    d.update(params_np(model))
+    f = model(x).detach()
+    g = ref_losses.compute_normal(model, x.clone()).detach()
+    d["f"], d["g"] = f.numpy()[:, 0], g.numpy()
+    loss = ref_losses.WeightedSmoothL2Loss(0.5, 0.1)(x.clone(), y, model, 0)
+    loss.backward()
+    d["wsl2_loss"] = np.float64(loss.item())
+    d.update(grads_np(model, "wsl2_grad_"))
+    loss_fn = ref_losses.IGRLOSS(0.1, 1.0, 0.1, 1.0)
+    loss = quiet(loss_fn, x.clone(), y, model, 0)
+    loss.backward()
+    d["igr_loss"] = np.float64(loss.item())
+    d.update(grads_np(model, "igr_grad_"))
+    np.savez_compressed(os.path.join(OUT, "relu_tanh_128x3.npz"), **d)
+
+
+def case_full():
+    # BASELINE configs 2-5 network: weights are NOT stored (7.36 MB); the drop-in's seed-identical init regenerates
+    # them (hash checked) -- SURVEY.md §8d cfg 2.
+    torch.manual_seed(0)
+    model = quiet(ref_networks.ImplicitNet, 3, [512] * 8, (4,), 100.0, True)
+    h = hashlib.sha256()
+    for v in model.state_dict().values():
+        h.update(v.numpy().tobytes())
+    x = points(512, 1)
+    y = orc.torus_labels(x)
+    f = model(x).detach()
+    g = ref_losses.compute_normal(model, x.clone()).detach()
+    loss_fn = ref_losses.IGRLOSS(0.1, 1.0, 0.1, 1.0)
+    loss = quiet(loss_fn, x.clone(), y, model, 0)
+    loss.backward()
+    gnorm = np.array([p.grad.norm().item() for p in model.parameters()])
+    gsum = np.array([p.grad.double().sum().item() for p in model.parameters()])
+    # a 9^3 grid through the reference's own coordinate construction (executor/executor.py:351-356)
+    ax = torch.linspace(-1, 1, 9)
+    xx, yy, zz = torch.meshgrid(ax, ax, ax, indexing="ij")
+    coords = torch.stack((xx, yy, zz), dim=-1).reshape(-1, 3)
+    grid = model(coords).detach().numpy().reshape(9, 9, 9)
+    np.savez_compressed(
+        os.path.join(OUT, "full_8x512_seed0.npz"), weights_sha256=np.array(h.hexdigest()), x=x.numpy(), y=y.numpy(),
+        f=f.numpy()[:, 0], g=g.numpy(), igr_loss=np.float64(loss.item()), igr_grad_norms=gnorm, igr_grad_sums=gsum,
+        grid9=grid,
+    )
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    case_softplus()
+    case_relu()
+    case_full()
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))

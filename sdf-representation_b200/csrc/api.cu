@@ -1,0 +1,685 @@
+// C ABI (include/sdfnet.h) over the kernels in chain.cu / dw.cu / aux.cu.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "../../include/sdfnet.h"
+#include "sdf_internal.h"
+
+namespace sdf {
+cudaError_t launch_chain(const ChainParams& p, int dtype, int num_sms, cudaStream_t stream);
+cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
+                                int k16, int kind, float scale, int dtype, cudaStream_t stream);
+cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream);
+cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int num_sms, cudaStream_t stream);
+cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
+                             float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
+                             int relu_tanh, float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             cudaStream_t stream);
+cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
+                             float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             cudaStream_t stream);
+cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream);
+cudaError_t launch_tanh_seeds(const float* f, const float* g, const float* fbar_in, const float* gbar_in, int64_t n,
+                              float* fbar, float* gbar, cudaStream_t stream);
+cudaError_t launch_unpack_grads(int H, int L, int skip, const float* main_acc, const float* zx_acc, const float* qg_acc,
+                                const float* as_acc, const float* adx_acc, const double* fbar_sum, long num_params,
+                                float* grads, float scale, cudaStream_t stream);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                        int step, cudaStream_t stream);
+cudaError_t launch_octree_flags(const float* sdf, int64_t n, float thresh, uint8_t* flags, cudaStream_t stream);
+cudaError_t launch_mc_classify(const float* sdf, int nx, int ny, int nz, uint8_t* cases, cudaStream_t stream);
+long compact_num_blocks(long n);
+cudaError_t launch_compact(const uint8_t* v, long n, int mode, const uint64_t* keys, long* out_idx, uint64_t* out_keys,
+                           long* total, long* scratch, cudaStream_t stream);
+}  // namespace sdf
+
+using namespace sdf;
+
+namespace {
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(x)                                                                                       \
+  do {                                                                                              \
+    cudaError_t e_ = (x);                                                                           \
+    if (e_ != cudaSuccess) return fail(static_cast<int>(e_), "%s: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+enum : int { PK_F0 = 0, PK_FH = 1, PK_FL = 2, PK_RH = 3, PK_R0 = 4 };
+
+struct StepImage {  // shape of one packed step image
+  int n_groups, ng, kchunks, k16;
+  uint32_t chunk_bytes, off;
+  uint32_t bytes() const { return static_cast<uint32_t>(n_groups) * kchunks * chunk_bytes; }
+};
+}  // namespace
+
+namespace sdf {
+// where the accumulated weight-gradient tiles live and how they map onto the parameter vector
+struct GradLayout {
+  int H, L, skip;
+  float* main_acc;    // [(L-1)][H (in)][H (out)]   layers 1..L-1
+  float* zx_acc;      // [L][16][H]   Zbar_l^T . Xblock     (col 15 -> db_l ; l = 0: cols 0..8 -> dW_0 term 1)
+  float* qg_acc;      // [16][H]      q_0^T . Gblock        (cols 0..8 -> dW_0 term 2)
+  float* as_acc;      // [16][H]      a_{L-1}^T . Sblock    (cols 0..2 -> dW_L term 1)
+  float* adx_acc;     // [16][H]      adot_{L-1}^T . Xblock (col 15 -> dW_L term 2)
+  double* fbar_sum;   // [1]          sum fbar -> db_L
+  int64_t num_params;
+};
+}  // namespace sdf
+
+struct sdfnet_handle {
+  sdfnet_desc d;
+  int H, L, skip, num_sms;
+  bool relu;
+  uint8_t* wpack = nullptr;
+  size_t wpack_bytes = 0;
+  float* bias = nullptr;
+  float* w_last = nullptr;
+  std::vector<StepImage> F, R;  // F[0..L], R[0..L-1]
+  // gradient accumulators
+  float* acc = nullptr;
+  size_t acc_floats = 0;
+  double* fbar_sum = nullptr;
+  GradLayout gl;
+  DwItem* items_dev = nullptr;
+  int items_cap = 0;
+  int items_n = 0;                 // cached work list: valid for (items_ws, items_tiles, items_so)
+  const void* items_ws = nullptr;
+  int items_tiles = -1;
+  int items_so = -1;
+  float* seeds = nullptr;  // scratch for f, g, fbar, gbar of one chunk (allocated on demand)
+  int64_t seeds_cap = 0;
+  float seed_scale = 1.f;
+};
+
+extern "C" const char* sdfnet_last_error(void) { return g_err; }
+
+static StepImage make_image(int N, int K16total, int kchunk_k16, uint32_t& off) {
+  StepImage s;
+  s.ng = N < 256 ? N : 256;
+  s.n_groups = N / s.ng;
+  s.k16 = kchunk_k16;
+  s.kchunks = K16total / kchunk_k16;
+  s.chunk_bytes = static_cast<uint32_t>(s.ng) * 16u * 2u * kchunk_k16;
+  s.off = off;
+  off += s.bytes();
+  return s;
+}
+
+extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
+  if (!desc || !out) return fail(1, "sdfnet_create: null argument");
+  if (desc->d_in != 3) return fail(1, "sdfnet_create: d_in must be 3 (got %d)", desc->d_in);
+  if (desc->hidden < 64 || desc->hidden > kMaxH || desc->hidden % 64)
+    return fail(1, "sdfnet_create: hidden width must be a multiple of 64 in [64,512] (got %d)", desc->hidden);
+  if (desc->num_hidden < 2 || desc->num_hidden > kMaxLayers)
+    return fail(1, "sdfnet_create: num_hidden must be in [2,%d] (got %d)", kMaxLayers, desc->num_hidden);
+  if (desc->skip_layer < 0 || desc->skip_layer == 1 || desc->skip_layer >= desc->num_hidden)
+    return fail(1, "sdfnet_create: skip layer must be 0 (none) or in [2,%d) (got %d)", desc->num_hidden, desc->skip_layer);
+  if (desc->dtype != DT_BF16 && desc->dtype != DT_FP16) return fail(1, "sdfnet_create: dtype must be 0 (bf16) or 1 (fp16)");
+  if (desc->precision != 0) return fail(1, "sdfnet_create: precision %d not available in this build", desc->precision);
+  if (!(desc->beta >= 0.f)) return fail(1, "sdfnet_create: beta must be >= 0");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (desc->device < 0 || desc->device >= ndev) return fail(1, "sdfnet_create: no CUDA device %d (no CPU fallback)", desc->device);
+  CU(cudaSetDevice(desc->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10) return fail(1, "sdfnet_create: device %d is sm_%d%d; this library is sm_100a only", desc->device, prop.major, prop.minor);
+
+  sdfnet_handle* h = new (std::nothrow) sdfnet_handle();
+  if (!h) return fail(2, "sdfnet_create: out of host memory");
+  h->d = *desc;
+  h->H = desc->hidden;
+  h->L = desc->num_hidden;
+  h->skip = desc->skip_layer;
+  h->relu = desc->beta == 0.f;
+  h->num_sms = prop.multiProcessorCount;
+  const int H = h->H, L = h->L;
+  uint32_t off = 0;
+  h->F.resize(L + 1);
+  h->R.resize(L);
+  h->F[0] = make_image(H, 1, 1, off);                     // K = 16 (split input block)
+  for (int l = 1; l < L; ++l) h->F[l] = make_image(H, H / 16, 4, off);
+  h->F[L] = make_image(16, H / 16, H / 16, off);          // N = 16 (row 0 = lin_L)
+  for (int l = L - 1; l >= 1; --l) h->R[l] = make_image(H, H / 16, 4, off);
+  h->R[0] = make_image(16, H / 16, H / 16, off);          // N = 16 (rows 0..2 = d/dx)
+  h->wpack_bytes = off;
+  CU(cudaMalloc(&h->wpack, h->wpack_bytes));
+  CU(cudaMalloc(&h->bias, sizeof(float) * (L + 1) * H));
+  CU(cudaMalloc(&h->w_last, sizeof(float) * H));
+  // gradient accumulators
+  const size_t n_main = static_cast<size_t>(L - 1) * H * H;
+  const size_t n_zx = static_cast<size_t>(L) * 16 * H;
+  h->acc_floats = n_main + n_zx + 3 * 16 * static_cast<size_t>(H);
+  CU(cudaMalloc(&h->acc, sizeof(float) * h->acc_floats));
+  CU(cudaMalloc(&h->fbar_sum, sizeof(double)));
+  CU(cudaMemset(h->acc, 0, sizeof(float) * h->acc_floats));
+  CU(cudaMemset(h->fbar_sum, 0, sizeof(double)));
+  GradLayout& gl = h->gl;
+  gl.H = H; gl.L = L; gl.skip = h->skip;
+  gl.main_acc = h->acc;
+  gl.zx_acc = gl.main_acc + n_main;
+  gl.qg_acc = gl.zx_acc + n_zx;
+  gl.as_acc = gl.qg_acc + 16 * H;
+  gl.adx_acc = gl.as_acc + 16 * H;
+  gl.fbar_sum = h->fbar_sum;
+  int64_t np = 0;
+  for (int l = 0; l <= L; ++l) {
+    const int in = l == 0 ? 3 : H;
+    const int outd = l == L ? 1 : ((h->skip > 0 && l + 1 == h->skip) ? H - 3 : H);
+    np += static_cast<int64_t>(outd) * in + outd;
+  }
+  gl.num_params = np;
+  *out = h;
+  return 0;
+}
+
+extern "C" int sdfnet_destroy(sdfnet_t h) {
+  if (!h) return 0;
+  cudaFree(h->wpack);
+  cudaFree(h->bias);
+  cudaFree(h->w_last);
+  cudaFree(h->acc);
+  cudaFree(h->fbar_sum);
+  cudaFree(h->items_dev);
+  cudaFree(h->seeds);
+  delete h;
+  return 0;
+}
+
+extern "C" int64_t sdfnet_num_params(sdfnet_t h) { return h ? h->gl.num_params : -1; }
+
+static int out_dim_of(const sdfnet_handle* h, int l) {
+  if (l == h->L) return 1;
+  return (h->skip > 0 && l + 1 == h->skip) ? h->H - 3 : h->H;
+}
+
+extern "C" int sdfnet_pack_weights(sdfnet_t h, const float* const* W, const float* const* b, void* stream_) {
+  if (!h || !W || !b) return fail(1, "sdfnet_pack_weights: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int H = h->H, L = h->L, dt = h->d.dtype;
+  const float c = static_cast<float>(1.0 / std::sqrt(2.0));
+  for (int l = 0; l <= L; ++l) {
+    if (!W[l] || !b[l]) return fail(1, "sdfnet_pack_weights: null parameter pointer for layer %d", l);
+    const StepImage& s = h->F[l];
+    const int kind = l == 0 ? PK_F0 : (l == L ? PK_FL : PK_FH);
+    const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
+    CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
+                           kind, scale, dt, stream));
+    CU(launch_pack_bias(b[l], out_dim_of(h, l), h->bias + static_cast<size_t>(l) * H, H, stream));
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    const StepImage& s = h->R[l];
+    const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
+    CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
+                           l == 0 ? PK_R0 : PK_RH, scale, dt, stream));
+  }
+  CU(cudaMemcpyAsync(h->w_last, W[L], sizeof(float) * H, cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// program construction
+// ------------------------------------------------------------------------------------------------
+static void add_step(ChainParams& p, int epi, int layer, const StepImage* img) {
+  StepDesc& s = p.steps[p.n_steps++];
+  s.epi = epi;
+  s.layer = layer;
+  if (img) {
+    s.n_groups = img->n_groups; s.ng = img->ng; s.kchunks = img->kchunks; s.k16 = img->k16;
+    s.chunk_bytes = img->chunk_bytes; s.w_off = img->off;
+  } else {
+    s.n_groups = 0; s.ng = 0; s.kchunks = 0; s.k16 = 0; s.chunk_bytes = 0; s.w_off = 0;
+  }
+}
+static void base_params(const sdfnet_handle* h, ChainParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.H = h->H; p.L = h->L; p.skip = h->skip;
+  p.beta = h->d.beta;
+  p.inv_beta = h->relu ? 0.f : 1.f / h->d.beta;
+  p.bias = h->bias; p.w_last = h->w_last; p.wpack = h->wpack;
+  p.flags = h->relu ? FL_RELU : 0u;
+}
+static void prog_forward(const sdfnet_handle* h, ChainParams& p) {
+  for (int l = 0; l < h->L; ++l) add_step(p, EPI_FWD_HIDDEN, l, &h->F[l]);
+  add_step(p, EPI_FWD_LAST, h->L, &h->F[h->L]);
+}
+static void prog_reverse(const sdfnet_handle* h, ChainParams& p) {
+  add_step(p, EPI_REV_START, h->L - 1, nullptr);
+  for (int l = h->L - 1; l >= 1; --l) add_step(p, EPI_REV_HIDDEN, l, &h->R[l]);
+  add_step(p, EPI_REV_LAST, 0, &h->R[0]);
+}
+static void prog_tangent(const sdfnet_handle* h, ChainParams& p) {
+  for (int l = 0; l < h->L; ++l) add_step(p, EPI_TAN_HIDDEN, l, &h->F[l]);
+}
+static void prog_adjoint(const sdfnet_handle* h, ChainParams& p) {
+  add_step(p, EPI_ADJ_START, h->L - 1, nullptr);
+  for (int l = h->L - 2; l >= 0; --l) add_step(p, EPI_ADJ_HIDDEN, l, &h->R[l + 1]);
+}
+
+// workspace carving -------------------------------------------------------------------------------
+namespace {
+struct Spill {
+  uint8_t *A, *Q, *AD, *U, *Z, *X, *G, *S;
+  float *f, *g, *fbar, *gbar;
+};
+size_t per_tile_bytes(const sdfnet_handle* h, int mode) {
+  const size_t ib = img_bytes(h->H);
+  if (mode == 0) return h->L * ib;
+  return 5 * h->L * ib + 3 * 2 * kGranuleBytes + kTileRows * 8 * sizeof(float);
+}
+// carve the workspace for `tiles` tiles
+void carve(const sdfnet_handle* h, int mode, uint8_t* ws, size_t tiles, Spill& s) {
+  const size_t ib = img_bytes(h->H);
+  const size_t arr = h->L * ib * tiles;
+  memset(&s, 0, sizeof(s));
+  s.A = ws; ws += arr;
+  if (mode == 0) return;
+  s.Q = ws; ws += arr;
+  s.AD = ws; ws += arr;
+  s.U = ws; ws += arr;
+  s.Z = ws; ws += arr;
+  s.X = ws; ws += tiles * 2 * kGranuleBytes;
+  s.G = ws; ws += tiles * 2 * kGranuleBytes;
+  s.S = ws; ws += tiles * 2 * kGranuleBytes;
+  s.f = reinterpret_cast<float*>(ws); ws += tiles * kTileRows * sizeof(float);
+  s.g = reinterpret_cast<float*>(ws); ws += tiles * kTileRows * 3 * sizeof(float);
+  s.fbar = reinterpret_cast<float*>(ws); ws += tiles * kTileRows * sizeof(float);
+  s.gbar = reinterpret_cast<float*>(ws); ws += tiles * kTileRows * 3 * sizeof(float);
+}
+}  // namespace
+
+extern "C" size_t sdfnet_workspace_bytes(sdfnet_t h, int64_t n_points, int32_t mode) {
+  if (!h || n_points <= 0) return 0;
+  const size_t tiles = static_cast<size_t>((n_points + kTileRows - 1) / kTileRows);
+  return tiles * per_tile_bytes(h, mode) + 1024;
+}
+
+static uint8_t* align_ws(void* ws, size_t& bytes) {
+  uintptr_t p = reinterpret_cast<uintptr_t>(ws);
+  uintptr_t a = (p + 255) & ~static_cast<uintptr_t>(255);
+  const size_t lost = a - p;
+  bytes = bytes > lost ? bytes - lost : 0;
+  return reinterpret_cast<uint8_t*>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// inference entry points
+// ------------------------------------------------------------------------------------------------
+static int run_forward(sdfnet_t h, ChainParams& p, int64_t n, cudaStream_t stream) {
+  p.n = n;
+  p.n_tiles = static_cast<int>((n + kTileRows - 1) / kTileRows);
+  prog_forward(h, p);
+  CU(launch_chain(p, h->d.dtype, h->num_sms, stream));
+  return 0;
+}
+
+extern "C" int sdfnet_forward(sdfnet_t h, const float* x, int64_t n, float* sdf_out, void* stream) {
+  if (!h || !x || !sdf_out) return fail(1, "sdfnet_forward: null argument");
+  if (n <= 0) return 0;
+  // tiles are counted in int32: split very large batches
+  const int64_t kMax = static_cast<int64_t>(1) << 30;
+  for (int64_t o = 0; o < n; o += kMax) {
+    ChainParams p;
+    base_params(h, p);
+    p.src = SRC_POINTS;
+    p.x = x + o * 3;
+    p.f_out = sdf_out + o;
+    const int64_t m = n - o < kMax ? n - o : kMax;
+    if (int rc = run_forward(h, p, m, static_cast<cudaStream_t>(stream))) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_grid_eval(sdfnet_t h, const float* axis, int32_t n_axis, int64_t first, int64_t count, float* sdf_out,
+                                void* stream) {
+  if (!h || !axis || !sdf_out) return fail(1, "sdfnet_grid_eval: null argument");
+  if (n_axis <= 0) return fail(1, "sdfnet_grid_eval: n_axis must be positive");
+  const int64_t total = static_cast<int64_t>(n_axis) * n_axis * n_axis;
+  if (first < 0 || count < 0 || first + count > total)
+    return fail(1, "sdfnet_grid_eval: range [%lld, %lld) outside the %d^3 grid", (long long)first, (long long)(first + count), n_axis);
+  const int64_t kMax = static_cast<int64_t>(1) << 30;
+  for (int64_t o = 0; o < count; o += kMax) {
+    ChainParams p;
+    base_params(h, p);
+    p.src = SRC_GRID;
+    p.axis = axis;
+    p.grid_n = n_axis;
+    p.grid_off = first + o;
+    p.f_out = sdf_out + o;
+    const int64_t m = count - o < kMax ? count - o : kMax;
+    if (int rc = run_forward(h, p, m, static_cast<cudaStream_t>(stream))) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_octree_level(sdfnet_t h, const uint64_t* keys, int64_t count, int32_t level, float band, float* sdf_out,
+                                   uint8_t* refine_flags, void* stream) {
+  if (!h || !keys || !sdf_out) return fail(1, "sdfnet_octree_level: null argument");
+  if (level < 0 || level > 20) return fail(1, "sdfnet_octree_level: level %d outside [0,20]", level);
+  if (count <= 0) return 0;
+  ChainParams p;
+  base_params(h, p);
+  p.src = SRC_OCTREE;
+  p.keys = keys;
+  p.level = level;
+  p.f_out = sdf_out;
+  if (int rc = run_forward(h, p, count, static_cast<cudaStream_t>(stream))) return rc;
+  if (refine_flags) {
+    const float thresh = band * ldexpf(2.f, -level);  // band * h_level, one fp32 rounding (oracle/octree.py)
+    CU(launch_octree_flags(sdf_out, count, thresh, refine_flags, static_cast<cudaStream_t>(stream)));
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float* sdf_out, float* grad_out, void* ws_,
+                                   size_t ws_bytes, void* stream) {
+  if (!h || !x || !grad_out) return fail(1, "sdfnet_forward_grad: null argument");
+  if (n <= 0) return 0;
+  uint8_t* ws = align_ws(ws_, ws_bytes);
+  const size_t ptb = per_tile_bytes(h, 0);
+  size_t cap_tiles = ws_bytes / ptb;
+  if (!ws_ || cap_tiles == 0) return fail(1, "sdfnet_forward_grad: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, ptb);
+  if (cap_tiles > (1u << 22)) cap_tiles = 1u << 22;
+  const int64_t chunk = static_cast<int64_t>(cap_tiles) * kTileRows;
+  for (int64_t o = 0; o < n; o += chunk) {
+    const int64_t m = n - o < chunk ? n - o : chunk;
+    ChainParams p;
+    base_params(h, p);
+    p.src = SRC_POINTS;
+    p.x = x + o * 3;
+    p.f_out = sdf_out ? sdf_out + o : nullptr;
+    p.g_out = grad_out + o * 3;
+    p.n = m;
+    p.n_tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    Spill s;
+    carve(h, 0, ws, p.n_tiles, s);
+    p.Aimg = s.A;
+    p.flags |= FL_SPILL_A;
+    prog_forward(h, p);
+    prog_reverse(h, p);
+    CU(launch_chain(p, h->d.dtype, h->num_sms, static_cast<cudaStream_t>(stream)));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training entry points
+// ------------------------------------------------------------------------------------------------
+namespace {
+// Build and run the weight-gradient work list for one chunk of `tiles` tiles.
+int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_t stream) {
+  const int H = h->H, L = h->L;
+  const uint32_t ib = img_bytes(H);
+  const uint32_t xb = 2 * kGranuleBytes;
+  const GradLayout& gl = h->gl;
+  if (h->items_ws == s.A && h->items_tiles == tiles && h->items_so == (second_order ? 1 : 0) && h->items_n > 0) {
+    CU(launch_dw(h->items_dev, h->items_n, h->d.dtype, h->num_sms, stream));
+    return 0;
+  }
+  std::vector<DwItem> items;
+  const int nmb = H / 128 > 0 ? H / 128 : 1;
+  if (H % 128) return fail(1, "training requires hidden width multiple of 128 (got %d)", H);
+  const int nb = H > 256 ? 256 : H;       // N per main item
+  const int nnh = H / nb;
+  const int types = (L - 1) * nmb * nnh + (L + 3) * nmb;
+  int ksplit = (8 * h->num_sms + types - 1) / types;
+  if (ksplit > tiles) ksplit = tiles;
+  if (ksplit < 1) ksplit = 1;
+  const size_t arr = static_cast<size_t>(ib) * tiles;  // bytes of one layer of one spill array
+  for (int sp = 0; sp < ksplit; ++sp) {
+    const uint32_t t0 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * sp / ksplit);
+    const uint32_t t1 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * (sp + 1) / ksplit);
+    if (t1 <= t0) continue;
+    for (int l = 1; l < L; ++l) {
+      for (int mb = 0; mb < nmb; ++mb)
+        for (int nh = 0; nh < nnh; ++nh) {
+          DwItem d{};
+          d.A1 = s.Z + arr * l;        d.B1 = s.A + arr * (l - 1);
+          if (second_order) { d.A2 = s.Q + arr * l; d.B2 = s.AD + arr * (l - 1); }
+          d.a_tstride = ib; d.b_tstride = ib;
+          d.a_off = static_cast<uint32_t>(mb) * 16 * kGranuleBytes;
+          d.b_off = static_cast<uint32_t>(nh) * (nb / 8) * kGranuleBytes;
+          d.n = nb; d.tile0 = t0; d.tile1 = t1; d.out_ld = H;
+          d.out = gl.main_acc + (static_cast<size_t>(l - 1) * H + static_cast<size_t>(nh) * nb) * H + mb * 128;
+          items.push_back(d);
+        }
+    }
+    for (int mb = 0; mb < nmb; ++mb) {
+      const uint32_t aoff = static_cast<uint32_t>(mb) * 16 * kGranuleBytes;
+      for (int l = 0; l < L; ++l) {   // Zbar_l^T . Xblock -> biases (col 15) and, for l = 0, dW_0 term 1
+        DwItem d{};
+        d.A1 = s.Z + arr * l; d.B1 = s.X; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
+        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H;
+        d.out = gl.zx_acc + static_cast<size_t>(l) * 16 * H + mb * 128;
+        items.push_back(d);
+      }
+      {  // a_{L-1}^T . Sblock -> dW_L term 1
+        DwItem d{};
+        d.A1 = s.A + arr * (L - 1); d.B1 = s.S; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
+        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.out = gl.as_acc + mb * 128;
+        items.push_back(d);
+      }
+      if (second_order) {
+        DwItem d{};  // q_0^T . Gblock -> dW_0 term 2
+        d.A1 = s.Q; d.B1 = s.G; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
+        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.out = gl.qg_acc + mb * 128;
+        items.push_back(d);
+        DwItem e{};  // adot_{L-1}^T . Xblock -> dW_L term 2 (col 15)
+        e.A1 = s.AD + arr * (L - 1); e.B1 = s.X; e.a_tstride = ib; e.b_tstride = xb; e.a_off = aoff; e.b_off = 0;
+        e.n = 16; e.tile0 = t0; e.tile1 = t1; e.out_ld = H; e.out = gl.adx_acc + mb * 128;
+        items.push_back(e);
+      }
+    }
+  }
+  const int n_items = static_cast<int>(items.size());
+  if (n_items > h->items_cap) {
+    CU(cudaStreamSynchronize(stream));  // a previous launch may still read the old list
+    cudaFree(h->items_dev);
+    h->items_dev = nullptr;
+    h->items_cap = 0;
+    CU(cudaMalloc(&h->items_dev, sizeof(DwItem) * n_items));
+    h->items_cap = n_items;
+  }
+  // the list is rebuilt per call from a pageable host vector: a synchronous copy keeps it simple and safe
+  CU(cudaMemcpyAsync(h->items_dev, items.data(), sizeof(DwItem) * n_items, cudaMemcpyHostToDevice, stream));
+  CU(cudaStreamSynchronize(stream));
+  h->items_n = n_items; h->items_ws = s.A; h->items_tiles = tiles; h->items_so = second_order ? 1 : 0;
+  CU(launch_dw(h->items_dev, n_items, h->d.dtype, h->num_sms, stream));
+  return 0;
+}
+
+// forward (+reverse) over one chunk, spilling what training needs
+int run_fg(sdfnet_t h, const float* x, int64_t m, const Spill& s, bool need_g, cudaStream_t stream) {
+  ChainParams p;
+  base_params(h, p);
+  p.src = SRC_POINTS;
+  p.x = x;
+  p.n = m;
+  p.n_tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+  p.f_out = s.f;
+  p.g_out = need_g ? s.g : nullptr;
+  p.Aimg = s.A; p.Qimg = s.Q; p.Ximg = s.X;
+  p.flags |= FL_SPILL_A | FL_SPILL_X | (need_g ? FL_SPILL_Q : 0u);
+  prog_forward(h, p);
+  if (need_g) prog_reverse(h, p);
+  CU(launch_chain(p, h->d.dtype, h->num_sms, stream));
+  return 0;
+}
+// tangent (+adjoint) sweeps over one chunk
+int run_ta(sdfnet_t h, int64_t m, const Spill& s, const float* fbar, const float* gbar, cudaStream_t stream) {
+  ChainParams p;
+  base_params(h, p);
+  p.n = m;
+  p.n_tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+  p.fbar = fbar; p.gbar = gbar;
+  p.Aimg = s.A; p.Qimg = s.Q; p.ADimg = s.AD; p.Uimg = s.U; p.Zimg = s.Z; p.Ximg = s.X; p.Gimg = s.G; p.Simg = s.S;
+  if (gbar) {
+    p.flags |= FL_TANGENT;
+    prog_tangent(h, p);
+  }
+  prog_adjoint(h, p);
+  CU(launch_chain(p, h->d.dtype, h->num_sms, stream));
+  return 0;
+}
+int64_t chunk_points(sdfnet_t h, size_t ws_bytes) {
+  size_t cap_tiles = ws_bytes / per_tile_bytes(h, 1);
+  if (cap_tiles > (1u << 22)) cap_tiles = 1u << 22;
+  return static_cast<int64_t>(cap_tiles) * kTileRows;
+}
+}  // namespace
+
+extern "C" int sdfnet_zero_grads(sdfnet_t h, void* stream) {
+  if (!h) return fail(1, "sdfnet_zero_grads: null handle");
+  CU(cudaMemsetAsync(h->acc, 0, sizeof(float) * h->acc_floats, static_cast<cudaStream_t>(stream)));
+  CU(cudaMemsetAsync(h->fbar_sum, 0, sizeof(double), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int sdfnet_read_grads(sdfnet_t h, float* grads, float scale, void* stream) {
+  if (!h || !grads) return fail(1, "sdfnet_read_grads: null argument");
+  const GradLayout& gl = h->gl;
+  CU(launch_unpack_grads(gl.H, gl.L, gl.skip, gl.main_acc, gl.zx_acc, gl.qg_acc, gl.as_acc, gl.adx_acc, gl.fbar_sum,
+                         gl.num_params, grads, scale / h->seed_scale, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int sdfnet_backward(sdfnet_t h, const float* x, int64_t n, const float* fbar, const float* gbar, void* ws_,
+                               size_t ws_bytes, void* stream_) {
+  if (!h || !x) return fail(1, "sdfnet_backward: null argument");
+  if (!fbar && !gbar) return 0;
+  if (n <= 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* ws = align_ws(ws_, ws_bytes);
+  const int64_t chunk = ws_ ? chunk_points(h, ws_bytes) : 0;
+  if (chunk <= 0) return fail(1, "sdfnet_backward: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, per_tile_bytes(h, 1));
+  for (int64_t o = 0; o < n; o += chunk) {
+    const int64_t m = n - o < chunk ? n - o : chunk;
+    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    Spill s;
+    carve(h, 1, ws, tiles, s);
+    // the ReLU/tanh network needs f (and g) to move the seeds through the output tanh
+    const bool need_g = gbar != nullptr;
+    if (int rc = run_fg(h, x + o * 3, m, s, need_g, stream)) return rc;
+    const float* fb = fbar ? fbar + o : nullptr;
+    const float* gb = gbar ? gbar + o * 3 : nullptr;
+    if (h->relu) {
+      CU(launch_tanh_seeds(s.f, s.g, fb, gb, m, s.fbar, s.gbar, stream));
+      fb = s.fbar;
+      gb = gbar ? s.gbar : nullptr;
+    }
+    if (fb) CU(launch_sum(fb, m, h->fbar_sum, stream));
+    if (int rc = run_ta(h, m, s, fb, gb, stream)) return rc;
+    if (int rc = run_dw(h, s, tiles, gbar != nullptr, stream)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_train_step_igr(sdfnet_t h, const float* x, const float* y, int64_t n, const sdfnet_igr_cfg* cfg,
+                                     double* loss_sums, void* ws_, size_t ws_bytes, void* stream_) {
+  if (!h || !x || !y || !cfg || !loss_sums) return fail(1, "sdfnet_train_step_igr: null argument");
+  if (n <= 0) return 0;
+  if (cfg->n_global <= 0) return fail(1, "sdfnet_train_step_igr: n_global must be positive");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* ws = align_ws(ws_, ws_bytes);
+  const int64_t chunk = ws_ ? chunk_points(h, ws_bytes) : 0;
+  if (chunk <= 0) return fail(1, "sdfnet_train_step_igr: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, per_tile_bytes(h, 1));
+  for (int64_t o = 0; o < n; o += chunk) {
+    const int64_t m = n - o < chunk ? n - o : chunk;
+    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    Spill s;
+    carve(h, 1, ws, tiles, s);
+    if (int rc = run_fg(h, x + o * 3, m, s, true, stream)) return rc;
+    CU(launch_igr_seeds(s.f, s.g, y + o * 4, m, cfg->delta, cfg->tau, cfg->lambda_g, cfg->regularizer_threshold,
+                        cfg->mean_t, cfg->mean_t_dev, 1.0 / static_cast<double>(cfg->n_global), cfg->data_term, h->relu ? 1 : 0,
+                        h->seed_scale, s.fbar, s.gbar, loss_sums, h->fbar_sum, stream));
+    if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
+    if (int rc = run_dw(h, s, tiles, true, stream)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int64_t n_global, const float* xp, int64_t m_,
+                                     int64_t m_global, float lambda_g, double* loss_sums, void* ws_, size_t ws_bytes,
+                                     void* stream_) {
+  if (!h || !loss_sums) return fail(1, "sdfnet_train_step_pcd: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* ws = align_ws(ws_, ws_bytes);
+  const int64_t chunk = ws_ ? chunk_points(h, ws_bytes) : 0;
+  if (chunk <= 0) return fail(1, "sdfnet_train_step_pcd: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, per_tile_bytes(h, 1));
+  // surface points: L += mean |f|   (first order: forward + adjoint + dW term 1)
+  for (int64_t o = 0; x && o < n; o += chunk) {
+    const int64_t m = n - o < chunk ? n - o : chunk;
+    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    Spill s;
+    carve(h, 1, ws, tiles, s);
+    if (int rc = run_fg(h, x + o * 3, m, s, false, stream)) return rc;
+    CU(launch_pcd_seeds(s.f, nullptr, m, 0, 1.f / static_cast<float>(n_global), h->relu ? 1 : 0, h->seed_scale, s.fbar,
+                        nullptr, loss_sums, h->fbar_sum, stream));
+    if (int rc = run_ta(h, m, s, s.fbar, nullptr, stream)) return rc;
+    if (int rc = run_dw(h, s, tiles, false, stream)) return rc;
+  }
+  // perturbed points: L += lambda mean (|grad f| - 1)^2
+  for (int64_t o = 0; xp && o < m_; o += chunk) {
+    const int64_t m = m_ - o < chunk ? m_ - o : chunk;
+    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    Spill s;
+    carve(h, 1, ws, tiles, s);
+    if (int rc = run_fg(h, xp + o * 3, m, s, true, stream)) return rc;
+    CU(launch_pcd_seeds(s.f, s.g, m, 1, lambda_g / static_cast<float>(m_global), h->relu ? 1 : 0, h->seed_scale, s.fbar,
+                        s.gbar, loss_sums, h->fbar_sum, stream));
+    if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
+    if (int rc = run_dw(h, s, tiles, true, stream)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                float beta1, float beta2, float eps, int32_t step, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail(1, "sdfnet_adam_step: null argument");
+  if (step < 1) return fail(1, "sdfnet_adam_step: step counts from 1");
+  CU(launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int sdfnet_mc_classify(const float* sdf, int32_t nx, int32_t ny, int32_t nz, uint8_t* case_index,
+                                  int64_t* active_cells, int64_t* n_active, void* stream_) {
+  if (!sdf || !case_index) return fail(1, "sdfnet_mc_classify: null argument");
+  if (nx < 2 || ny < 2 || nz < 2) return fail(1, "sdfnet_mc_classify: block must be at least 2x2x2");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CU(launch_mc_classify(sdf, nx, ny, nz, case_index, stream));
+  if (active_cells && n_active) {
+    const long total = static_cast<long>(nx - 1) * (ny - 1) * (nz - 1);
+    long* scratch = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(long) * (compact_num_blocks(total) + 1), stream));
+    static_assert(sizeof(long) == sizeof(int64_t), "LP64 expected");
+    cudaError_t e = launch_compact(case_index, total, 0, nullptr, reinterpret_cast<long*>(active_cells), nullptr,
+                                   reinterpret_cast<long*>(n_active), scratch, stream);
+    cudaFreeAsync(scratch, stream);
+    CU(e);
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_octree_refine(const uint64_t* keys, const uint8_t* flags, int64_t count, uint64_t* child_keys,
+                                    int64_t* n_children, void* stream_) {
+  if (!keys || !flags || !child_keys || !n_children) return fail(1, "sdfnet_octree_refine: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  long* scratch = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(long) * (compact_num_blocks(count) + 1), stream));
+  // n_children receives the number of refined CELLS; each contributes 8 consecutive child keys
+  cudaError_t e = launch_compact(flags, count, 1, keys, nullptr, child_keys, reinterpret_cast<long*>(n_children), scratch, stream);
+  cudaFreeAsync(scratch, stream);
+  CU(e);
+  return 0;
+}

@@ -1,0 +1,496 @@
+// Auxiliary kernels around the layer chain: weight packing into UMMA operand images, loss seeds and
+// reductions (IGRLOSS / point-cloud / WeightedSmoothL2), gradient unpacking, fused Adam, marching-cubes cell
+// classification and octree refinement.  All plain CUDA-core kernels: they are HBM- or latency-bound.
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include "sdf_internal.h"
+
+namespace sdf {
+
+__device__ __forceinline__ float rnd16(float v, int dtype) {
+  return dtype == DT_BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
+}
+__device__ __forceinline__ uint16_t bits16(float v, int dtype) {
+  if (dtype == DT_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing.  One launch per step image.  Destination element order (see chain.cu MMA loop):
+//   [group g][k-chunk kc][granule gr (2*k16 per chunk)][row (ng)][8 elements]
+// logical operand B[n][k] with n = g*ng + row, k = (kc*2*k16 + gr)*8 + e.
+// ------------------------------------------------------------------------------------------------
+enum : int { PK_F0 = 0, PK_FH = 1, PK_FL = 2, PK_RH = 3, PK_R0 = 4 };
+
+__global__ void pack_weights_kernel(const float* __restrict__ W, int out_dim, int in_dim, uint16_t* __restrict__ dst,
+                                    int n_groups, int ng, int kchunks, int k16, int kind, float scale, int dtype) {
+  const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    long t = idx;
+    const int e = static_cast<int>(t % 8); t /= 8;
+    const int row = static_cast<int>(t % ng); t /= ng;
+    const int gr = static_cast<int>(t % (2 * k16)); t /= (2 * k16);
+    const int kc = static_cast<int>(t % kchunks); t /= kchunks;
+    const int g = static_cast<int>(t);
+    const int n = g * ng + row;
+    const int k = (kc * 2 * k16 + gr) * 8 + e;
+    float v = 0.f;
+    switch (kind) {
+      case PK_F0: {  // layer 0 forward: W [H][3] against the split input block
+        if (n < out_dim && k < 15) {
+          const float w = W[n * in_dim + (k % 3)];
+          const float hi = rnd16(w, dtype);
+          v = (k < 9) ? hi : rnd16(w - hi, dtype);
+        }
+      } break;
+      case PK_FH:
+        if (n < out_dim && k < in_dim) v = scale * W[static_cast<long>(n) * in_dim + k];
+        break;
+      case PK_FL:
+        if (n == 0 && k < in_dim) v = W[k];
+        break;
+      case PK_RH:  // B[n = input feature][k = output feature]
+        if (k < out_dim && n < in_dim) v = scale * W[static_cast<long>(k) * in_dim + n];
+        break;
+      case PK_R0:  // W_0 [H][3] transposed: n = coordinate, k = feature
+        if (n < in_dim && k < out_dim) v = W[k * in_dim + n];
+        break;
+    }
+    dst[idx] = bits16(v, dtype);
+  }
+}
+
+__global__ void pack_bias_kernel(const float* __restrict__ b, int out_dim, float* __restrict__ dst, int H) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x) dst[i] = i < out_dim ? b[i] : 0.f;
+}
+
+cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
+                                int k16, int kind, float scale, int dtype, cudaStream_t stream) {
+  const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  pack_weights_kernel<<<blocks, 256, 0, stream>>>(W, out_dim, in_dim, static_cast<uint16_t*>(dst), n_groups, ng, kchunks,
+                                                  k16, kind, scale, dtype);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream) {
+  pack_bias_kernel<<<(H + 255) / 256, 256, 0, stream>>>(b, out_dim, dst, H);
+  return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Loss seeds.  Per point: (f, g) -> (fbar, gbar) = dL/df, dL/dg and the partial sums of the loss terms.
+// Block-level warp-shuffle trees, one double atomicAdd per block and term.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NS>
+__device__ __forceinline__ void block_accumulate(float (&v)[NS], double* sums) {
+  __shared__ float part[NS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    float w = warp_sum(v[i]);
+    if (lane == 0) part[i][warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      float w = lane < nw ? part[i][lane] : 0.f;
+      w = warp_sum(w);
+      if (lane == 0) atomicAdd(&sums[i], static_cast<double>(w));
+    }
+  }
+}
+
+struct IgrCfgDev {
+  float delta, tau, lambda_g, thr, mean_t, inv_n;
+  int data_term, relu_tanh;
+  float seed_scale;
+  const float* mean_t_dev;
+};
+
+// reference model/losses.py:109-137 (IGRLOSS.forward) differentiated by hand:
+//   p = clamp(f, +-delta), t = clamp(S, +-delta), m = |t| < thr
+//   cos = n.g / (max(|n|,1e-8) max(|g|,1e-8));  reg = m ? (1-cos)^2 : 1e-8;  eik = m ? (|g|-1)^2 : 1e-8
+//   L = D + tau mean(reg) + lambda mean(eik),  D = mean(p^2)+mean(t^2)-2 mean(p) mean(t)  |  mean((p-t)^2)
+__global__ void igr_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ y,
+                                 long n, IgrCfgDev c, float* __restrict__ fbar, float* __restrict__ gbar,
+                                 double* __restrict__ sums) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c.mean_t_dev) c.mean_t = __ldg(c.mean_t_dev);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float fi = f[i];
+    const float gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
+    const float4 yi = __ldg(reinterpret_cast<const float4*>(y) + i);
+    const float p = fminf(fmaxf(fi, -c.delta), c.delta);
+    const float t = fminf(fmaxf(yi.x, -c.delta), c.delta);
+    const bool inside = (fi >= -c.delta) && (fi <= c.delta);
+    const bool m = fabsf(t) < c.thr;
+    const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+    const float nn = sqrtf(yi.y * yi.y + yi.z * yi.z + yi.w * yi.w);
+    const float gnc = fmaxf(gn, 1e-8f), nnc = fmaxf(nn, 1e-8f);
+    const float dot = yi.y * gx + yi.z * gy + yi.w * gz;
+    const float cs = dot / (nnc * gnc);
+    const float reg = m ? (1.f - cs) * (1.f - cs) : 1e-8f;
+    const float eik = m ? (gn - 1.f) * (gn - 1.f) : 1e-8f;
+    acc[0] += p; acc[1] += p * p; acc[2] += t; acc[3] += t * t; acc[4] += (p - t) * (p - t);
+    acc[5] += reg; acc[6] += eik; acc[7] += 1.f;
+    // seeds
+    float fb = inside ? 2.f * c.inv_n * (p - (c.data_term == 0 ? c.mean_t : t)) : 0.f;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    if (m) {
+      // d(1-cos)^2/dg = -2 (1-cos) dcos/dg ; dcos/dg = n/(|n||g|) - cos g/|g|^2   (|g| above the eps clamp)
+      const float k1 = -2.f * c.tau * c.inv_n * (1.f - cs);
+      const float inv_ng = 1.f / (nnc * gnc);
+      const float k2 = gn > 1e-8f ? cs / (gn * gn) : 0.f;
+      // d(|g|-1)^2/dg = 2 (|g|-1) g/|g|
+      const float k3 = gn > 0.f ? 2.f * c.lambda_g * c.inv_n * (gn - 1.f) / gn : 0.f;
+      bx = k1 * (yi.y * inv_ng - k2 * gx) + k3 * gx;
+      by = k1 * (yi.z * inv_ng - k2 * gy) + k3 * gy;
+      bz = k1 * (yi.w * inv_ng - k2 * gz) + k3 * gz;
+    }
+    if (c.relu_tanh) {
+      // f = tanh(z), g = (1-f^2) G: seeds of the linear-output network are
+      //   zbar = fbar (1-f^2) - 2 f (gbar . g),   Gbar = (1-f^2) gbar
+      const float d = 1.f - fi * fi;
+      fb = fb * d - 2.f * fi * (bx * gx + by * gy + bz * gz);
+      bx *= d; by *= d; bz *= d;
+    }
+    fbar[i] = fb * c.seed_scale;
+    gbar[3 * i] = bx * c.seed_scale; gbar[3 * i + 1] = by * c.seed_scale; gbar[3 * i + 2] = bz * c.seed_scale;
+  }
+  block_accumulate<8>(acc, sums);
+}
+
+// reference executor/executordistributed.py:73-79:  which = 0: surface points, L += mean |f|  (fbar = sign(f)/N);
+// which = 1: perturbed points, L += lambda mean (|g|-1)^2  (gbar = (lambda/M) 2 (|g|-1) g/|g|).  coef = 1/N or lambda/M.
+__global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, long n, int which, float coef,
+                                 int relu_tanh, float seed_scale, float* __restrict__ fbar, float* __restrict__ gbar,
+                                 double* __restrict__ sums) {
+  float acc[1] = {0.f};
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float fi = f[i];
+    float fb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (which == 0) {
+      acc[0] += fabsf(fi);
+      fb = fi > 0.f ? coef : (fi < 0.f ? -coef : 0.f);
+    } else {
+      gx = g[3 * i]; gy = g[3 * i + 1]; gz = g[3 * i + 2];
+      const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+      acc[0] += (gn - 1.f) * (gn - 1.f);
+      const float k3 = gn > 0.f ? 2.f * coef * (gn - 1.f) / gn : 0.f;
+      bx = k3 * gx; by = k3 * gy; bz = k3 * gz;
+    }
+    if (relu_tanh) {
+      const float d = 1.f - fi * fi;
+      fb = fb * d - 2.f * fi * (bx * gx + by * gy + bz * gz);
+      bx *= d; by *= d; bz *= d;
+    }
+    fbar[i] = fb * seed_scale;
+    if (gbar) { gbar[3 * i] = bx * seed_scale; gbar[3 * i + 1] = by * seed_scale; gbar[3 * i + 2] = bz * seed_scale; }
+  }
+  block_accumulate<1>(acc, sums + which);
+}
+
+__global__ void sum_kernel(const float* __restrict__ v, long n, double* __restrict__ out) {
+  float acc[1] = {0.f};
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) acc[0] += v[i];
+  block_accumulate<1>(acc, out);
+}
+
+static int seed_blocks(long n) {
+  long b = (n + 255) / 256;
+  if (b > 2368) b = 2368;  // 16 blocks per SM
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
+                             float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
+                             int relu_tanh, float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             cudaStream_t stream) {
+  IgrCfgDev c;
+  c.mean_t_dev = mean_t_dev;
+  c.delta = delta; c.tau = tau; c.lambda_g = lambda_g; c.thr = thr; c.mean_t = mean_t;
+  c.inv_n = static_cast<float>(inv_n); c.data_term = data_term; c.relu_tanh = relu_tanh; c.seed_scale = seed_scale;
+  igr_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, y, n, c, fbar, gbar, sums);
+  sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(fbar, n, fbar_sum);
+  return cudaGetLastError();
+}
+cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
+                             float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             cudaStream_t stream) {
+  pcd_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, n, which, coef, relu_tanh, seed_scale, fbar, gbar, sums);
+  sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(fbar, n, fbar_sum);
+  return cudaGetLastError();
+}
+// ReLU/tanh network: turn seeds w.r.t. (f = tanh z, g = (1-f^2) G) into seeds w.r.t. (z, G), see igr_seeds_kernel.
+__global__ void tanh_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ fbar_in,
+                                  const float* __restrict__ gbar_in, long n, float* __restrict__ fbar, float* __restrict__ gbar) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float fi = f[i];
+    const float d = 1.f - fi * fi;
+    float fb = fbar_in ? fbar_in[i] * d : 0.f;
+    if (gbar_in) {
+      const float bx = gbar_in[3 * i], by = gbar_in[3 * i + 1], bz = gbar_in[3 * i + 2];
+      fb -= 2.f * fi * (bx * g[3 * i] + by * g[3 * i + 1] + bz * g[3 * i + 2]);
+      gbar[3 * i] = bx * d; gbar[3 * i + 1] = by * d; gbar[3 * i + 2] = bz * d;
+    }
+    fbar[i] = fb;
+  }
+}
+cudaError_t launch_tanh_seeds(const float* f, const float* g, const float* fbar_in, const float* gbar_in, int64_t n,
+                              float* fbar, float* gbar, cudaStream_t stream) {
+  tanh_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, fbar_in, gbar_in, n, fbar, gbar);
+  return cudaGetLastError();
+}
+cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream) {
+  sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(v, n, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient unpack: accumulator tiles -> flat parameter-gradient vector in state_dict order
+// (lin0.weight [out0,3], lin0.bias, lin1.weight [out1,H], ...; reference model/networks.py:62,77).
+// ------------------------------------------------------------------------------------------------
+struct GradLayoutDev {
+  int H, L, skip;
+  const float* main_acc; const float* zx_acc; const float* qg_acc; const float* as_acc; const float* adx_acc;
+  const double* fbar_sum;
+};
+
+__global__ void unpack_grads_kernel(GradLayoutDev gl, float* __restrict__ grads, long num_params, float scale) {
+  const int H = gl.H, L = gl.L;
+  const float c = 0.70710678118654752440f;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < num_params; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    long rem = idx;
+    float v = 0.f;
+    for (int l = 0; l <= L; ++l) {
+      const int in = l == 0 ? 3 : H;
+      const int outd = l == L ? 1 : ((gl.skip > 0 && l + 1 == gl.skip) ? H - 3 : H);
+      const long wsz = static_cast<long>(outd) * in;
+      if (rem < wsz) {
+        const int m = static_cast<int>(rem / in), n = static_cast<int>(rem % in);
+        if (l == 0) {
+          const float* zx = gl.zx_acc;  // layer 0 block: [16][H]
+          v = zx[(n) * H + m] + zx[(n + 3) * H + m] + zx[(n + 6) * H + m] + gl.qg_acc[(n) * H + m] +
+              gl.qg_acc[(n + 3) * H + m] + gl.qg_acc[(n + 6) * H + m];
+        } else if (l == L) {
+          v = gl.as_acc[0 * H + n] + gl.as_acc[1 * H + n] + gl.as_acc[2 * H + n] + gl.adx_acc[15 * H + n];
+        } else {
+          v = gl.main_acc[(static_cast<long>(l - 1) * H + n) * H + m];
+          if (gl.skip > 0 && l == gl.skip) v *= c;
+        }
+        break;
+      }
+      rem -= wsz;
+      if (rem < outd) {
+        const int m = static_cast<int>(rem);
+        v = l == L ? static_cast<float>(*gl.fbar_sum) : gl.zx_acc[(static_cast<long>(l) * 16 + 15) * H + m];
+        break;
+      }
+      rem -= outd;
+    }
+    grads[idx] = v * scale;
+  }
+}
+
+cudaError_t launch_unpack_grads(int H, int L, int skip, const float* main_acc, const float* zx_acc, const float* qg_acc,
+                                const float* as_acc, const float* adx_acc, const double* fbar_sum, long num_params,
+                                float* grads, float scale, cudaStream_t stream) {
+  GradLayoutDev gl{H, L, skip, main_acc, zx_acc, qg_acc, as_acc, adx_acc, fbar_sum};
+  unpack_grads_kernel<<<1184, 256, 0, stream>>>(gl, grads, num_params, scale);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam defaults: no amsgrad, no weight decay; reference executor/executor.py:160,177)
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                        int step, cudaStream_t stream) {
+  const float bc1 = 1.f - powf(b1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(b2, static_cast<float>(step));
+  adam_kernel<<<1184, 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, sqrtf(bc2));
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Octree refinement flags, marching-cubes cell classification, ordered stream compaction.
+// Integer / predicate work: bit-exact against oracle/octree.py and oracle/marching.py given equal SDF inputs.
+// ------------------------------------------------------------------------------------------------
+__global__ void octree_flags_kernel(const float* __restrict__ sdf, long n, float thresh, uint8_t* __restrict__ flags) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    flags[i] = fabsf(sdf[i]) <= thresh ? 1 : 0;
+}
+cudaError_t launch_octree_flags(const float* sdf, int64_t n, float thresh, uint8_t* flags, cudaStream_t stream) {
+  octree_flags_kernel<<<seed_blocks(n), 256, 0, stream>>>(sdf, n, thresh, flags);
+  return cudaGetLastError();
+}
+
+// corner c of cell (i,j,k): Lorensen-Cline order (0,0,0),(1,0,0),(1,1,0),(0,1,0),(0,0,1),(1,0,1),(1,1,1),(0,1,1)
+__global__ void mc_classify_kernel(const float* __restrict__ sdf, int nx, int ny, int nz, uint8_t* __restrict__ cases) {
+  const long cx = nx - 1, cy = ny - 1, cz = nz - 1;
+  const long total = cx * cy * cz;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long k = idx % cz, j = (idx / cz) % cy, i = idx / (cz * cy);
+    const float* b = sdf + (i * ny + j) * static_cast<long>(nz) + k;
+    const long sx = static_cast<long>(ny) * nz, sy = nz;
+    unsigned m = 0;
+    m |= (b[0] < 0.f) << 0;
+    m |= (b[sx] < 0.f) << 1;
+    m |= (b[sx + sy] < 0.f) << 2;
+    m |= (b[sy] < 0.f) << 3;
+    m |= (b[1] < 0.f) << 4;
+    m |= (b[sx + 1] < 0.f) << 5;
+    m |= (b[sx + sy + 1] < 0.f) << 6;
+    m |= (b[sy + 1] < 0.f) << 7;
+    cases[idx] = static_cast<uint8_t>(m);
+  }
+}
+
+// Ordered compaction in three passes: per-block counts, scan of the block counts (one block), scatter.
+constexpr int kScanBlock = 1024;
+constexpr int kItemsPerThread = 4;
+constexpr int kTileItems = kScanBlock * kItemsPerThread;
+
+// mode 0: flag = cases[i] not in {0,255};  mode 1: flag = flags[i] != 0
+__device__ __forceinline__ int compact_flag(const uint8_t* v, long i, int mode) {
+  const unsigned c = v[i];
+  return mode == 0 ? (c != 0u && c != 255u) : (c != 0u);
+}
+__global__ void compact_count_kernel(const uint8_t* __restrict__ v, long n, int mode, long* __restrict__ block_counts) {
+  __shared__ int wsum[32];
+  const long base = static_cast<long>(blockIdx.x) * kTileItems;
+  int c = 0;
+  for (int t = 0; t < kItemsPerThread; ++t) {
+    const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+    if (i < n) c += compact_flag(v, i, mode);
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = wsum[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = w;
+  }
+}
+__global__ void compact_scan_kernel(long* __restrict__ block_counts, long nblocks, long* __restrict__ total) {
+  // single block, sequential over chunks of blockDim.x; exclusive scan in place
+  __shared__ long sh[kScanBlock];
+  __shared__ long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long b0 = 0; b0 < nblocks; b0 += kScanBlock) {
+    const long i = b0 + threadIdx.x;
+    const long x = i < nblocks ? block_counts[i] : 0;
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+      long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nblocks) block_counts[i] = carry + sh[threadIdx.x] - x;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sh[kScanBlock - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+// mode 0: out[rank] = i (active cell index);  mode 1: out[8*rank + c] = (keys[i] << 3) | c
+__global__ void compact_scatter_kernel(const uint8_t* __restrict__ v, long n, int mode, const long* __restrict__ block_offsets,
+                                       const uint64_t* __restrict__ keys, long* __restrict__ out_idx,
+                                       uint64_t* __restrict__ out_keys) {
+  __shared__ int wsum[32];
+  const long base = static_cast<long>(blockIdx.x) * kTileItems;
+  int fl[kItemsPerThread];
+  int c = 0;
+  for (int t = 0; t < kItemsPerThread; ++t) {
+    const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+    fl[t] = i < n ? compact_flag(v, i, mode) : 0;
+    c += fl[t];
+  }
+  // exclusive scan of c over the block
+  int incl = c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+    int wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    wsum[lane] = wi - w;
+  }
+  __syncthreads();
+  long pos = block_offsets[blockIdx.x] + wsum[warp] + (incl - c);
+  for (int t = 0; t < kItemsPerThread; ++t) {
+    if (fl[t]) {
+      const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+      if (mode == 0) {
+        out_idx[pos] = i;
+      } else {
+        const uint64_t k = keys[i];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) out_keys[pos * 8 + ch] = (k << 3) | static_cast<uint64_t>(ch);
+      }
+      ++pos;
+    }
+  }
+}
+
+cudaError_t launch_mc_classify(const float* sdf, int nx, int ny, int nz, uint8_t* cases, cudaStream_t stream) {
+  const long total = static_cast<long>(nx - 1) * (ny - 1) * (nz - 1);
+  if (total <= 0) return cudaSuccess;
+  mc_classify_kernel<<<seed_blocks(total), 256, 0, stream>>>(sdf, nx, ny, nz, cases);
+  return cudaGetLastError();
+}
+// scratch: (nblocks) longs
+long compact_num_blocks(long n) { return (n + kTileItems - 1) / kTileItems; }
+cudaError_t launch_compact(const uint8_t* v, long n, int mode, const uint64_t* keys, long* out_idx, uint64_t* out_keys,
+                           long* total, long* scratch, cudaStream_t stream) {
+  const long nb = compact_num_blocks(n);
+  if (nb == 0) return cudaMemsetAsync(total, 0, sizeof(long), stream);
+  compact_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(v, n, mode, scratch);
+  compact_scan_kernel<<<1, kScanBlock, 0, stream>>>(scratch, nb, total);
+  compact_scatter_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(v, n, mode, scratch, keys, out_idx, out_keys);
+  return cudaGetLastError();
+}
+
+}  // namespace sdf

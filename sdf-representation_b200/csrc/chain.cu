@@ -1,0 +1,537 @@
+// Layer-chain kernel: one persistent CTA per SM walks 128-point tiles through a *program* of layer GEMMs
+// (tcgen05.mma, fp32 accumulators in TMEM) whose epilogues apply the activation / derivative math and write
+// the next A operand straight back into shared memory, so point activations never leave the SM inside a sweep.
+//
+// The same kernel runs four sweeps of the hot path (reference model/networks.py:87-106,
+// model/losses.py:283-296):
+//   forward            z_l = W_l h_l + b_l, a_l = act(z_l)                   (EPI_FWD_*)
+//   reverse            q_{l-1} = act'(z_{l-1}) * (W_l^T q_l)   -> g = grad_x f (EPI_REV_*)
+//   tangent            adot_l = act'(z_l) * (W_l hdot_l)                     (EPI_TAN_*)
+//   adjoint            Zbar_l = act'(z_l) * (W_{l+1}^T Zbar_{l+1}) + u_l     (EPI_ADJ_*)
+// State that must survive between sweeps (a_l, q_l, adot_l, u_l, Zbar_l) is spilled as operand images that the
+// weight-gradient kernel (dw.cu) consumes directly.
+//
+// Warp roles (320 threads): warps 0-7 epilogue (warp e owns TMEM lanes 32*(e%4).., columns half e/4 of each
+// 64-column block), warp 8 weight producer (cp.async.bulk into a 3-stage ring), warp 9 MMA issuer.
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include "ptx.cuh"
+#include "sdf_internal.h"
+
+namespace sdf {
+
+constexpr int kNumStages = 3;
+constexpr int kEpiThreads = 256;
+constexpr int kChainThreads = 320;
+constexpr uint32_t kABytes = kMaxH / 8 * kGranuleBytes;  // 131072
+constexpr uint32_t kChainSmem = kABytes + kNumStages * kStageBytes + 128 /*barriers*/ + kTileRows * 3 * 4 /*gskip*/;
+
+template <int DT>
+struct H16;
+template <>
+struct H16<DT_FP16> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+  static __device__ __forceinline__ float rnd(float a) { return __half2float(__float2half_rn(a)); }
+};
+template <>
+struct H16<DT_BF16> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+  static __device__ __forceinline__ float rnd(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+};
+
+__device__ __forceinline__ void st_smem_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_smem_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int DT>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 o;
+  o.x = H16<DT>::pack(v[0], v[1]);
+  o.y = H16<DT>::pack(v[2], v[3]);
+  o.z = H16<DT>::pack(v[4], v[5]);
+  o.w = H16<DT>::pack(v[6], v[7]);
+  return o;
+}
+template <int DT>
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  float2 t;
+  t = H16<DT>::unpack(u.x); v[0] = t.x; v[1] = t.y;
+  t = H16<DT>::unpack(u.y); v[2] = t.x; v[3] = t.y;
+  t = H16<DT>::unpack(u.z); v[4] = t.x; v[5] = t.y;
+  t = H16<DT>::unpack(u.w); v[6] = t.x; v[7] = t.y;
+}
+
+// Split a float into three 16-bit terms hi + lo + lolo (exact to ~fp32 for bf16, beyond for fp16).
+template <int DT>
+__device__ __forceinline__ void split3(float x, float& h, float& l, float& ll) {
+  h = H16<DT>::rnd(x);
+  float r1 = x - h;
+  l = H16<DT>::rnd(r1);
+  ll = H16<DT>::rnd(r1 - l);
+}
+
+// act(z): torch.nn.Softplus(beta, threshold=20) / ReLU.  For beta*z > 20 the softplus expression below differs
+// from the reference's linear branch by < 2.1e-9/beta, far under fp32 resolution of z.
+__device__ __forceinline__ float act_fwd(float z, float beta, float inv_beta, bool relu) {
+  if (relu) return fmaxf(z, 0.f);
+  float e = __expf(-fabsf(beta * z));
+  return fmaxf(z, 0.f) + __logf(1.f + e) * inv_beta;
+}
+// exp(-beta*a) = 1 - sigmoid(beta z) recovered from the stored activation a = softplus(z); relu: [a <= 0].
+__device__ __forceinline__ float act_em(float a, float beta, bool relu) {
+  if (relu) return a > 0.f ? 0.f : 1.f;
+  return __expf(-beta * a);
+}
+
+// Per-thread epilogue context
+struct Epi {
+  uint32_t sA;      // shared address of the A image
+  uint32_t taddr;   // TMEM base + this warp's lane quarter
+  int row;          // tile row == TMEM lane
+  int h;            // column half within each 64-column block
+  int64_t grow;     // global point index
+  bool valid;
+  size_t tile;
+  float x[3];       // input point (forward) or g-bar (tangent)
+  float fb;         // f-bar (adjoint start)
+  float fval;       // network output of this row (kept for the tanh mode)
+};
+
+template <int DT>
+__device__ __forceinline__ void store_chunk(const Epi& e, int c0, const float (&v)[32], uint8_t* img, bool to_smem) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 pk = pack8<DT>(&v[8 * j]);
+    uint32_t off = static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + e.row * 16;
+    if (to_smem) st_smem_v4(e.sA + off, pk);
+    if (img) *reinterpret_cast<uint4*>(img + off) = pk;
+  }
+}
+template <int DT>
+__device__ __forceinline__ void load_chunk_global(const Epi& e, int c0, const uint8_t* img, float (&v)[32]) {
+  uint4 pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    pk[j] = *reinterpret_cast<const uint4*>(img + static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + e.row * 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) unpack8<DT>(pk[j], &v[8 * j]);
+}
+template <int DT>
+__device__ __forceinline__ void load_chunk_smem(const Epi& e, int c0, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 pk = ld_smem_v4(e.sA + static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + e.row * 16);
+    unpack8<DT>(pk, &v[8 * j]);
+  }
+}
+__device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&b)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
+    b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load_acc32(const Epi& e, int c0, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(e.taddr + c0, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ uint8_t* img_ptr(uint8_t* base, int layer, int n_tiles, size_t tile, uint32_t ib) {
+  return base + (static_cast<size_t>(layer) * n_tiles + tile) * ib;
+}
+
+// Build the 16-column input block of one row: cols 0-2 hi, 3-5 lo, 6-8 lolo, 9-11 hi, 12-14 lo, 15 = last.
+// (The matching layer-0 weight columns are W_hi x3, W_lo x2, 0: the product reproduces fp32 x . W to ~2^-22.)
+template <int DT>
+__device__ __forceinline__ uint4 xblock_granule(const float (&x)[3], int h, float last) {
+  float hi[3], lo[3], ll[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) split3<DT>(x[j], hi[j], lo[j], ll[j]);
+  float v[8];
+  if (h == 0) {
+    v[0] = hi[0]; v[1] = hi[1]; v[2] = hi[2]; v[3] = lo[0]; v[4] = lo[1]; v[5] = lo[2]; v[6] = ll[0]; v[7] = ll[1];
+  } else {
+    v[0] = ll[2]; v[1] = hi[0]; v[2] = hi[1]; v[3] = hi[2]; v[4] = lo[0]; v[5] = lo[1]; v[6] = lo[2]; v[7] = last;
+  }
+  return pack8<DT>(v);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kNumStages * kStageBytes);
+  uint64_t* w_full = bars;                  // [kNumStages]
+  uint64_t* w_empty = bars + kNumStages;    // [kNumStages]
+  uint64_t* acc_full = bars + 2 * kNumStages;
+  uint64_t* a_ready = bars + 2 * kNumStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 2);
+  float* gskip = reinterpret_cast<float*>(smem + kABytes + kNumStages * kStageBytes + 128);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(a_ready, kEpiThreads);
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t ib = img_bytes(p.H);
+  const bool relu = (p.flags & FL_RELU) != 0;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t stage = 0, round = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < p.n_steps; ++s) {
+          const StepDesc& st = p.steps[s];
+          const int nchunks = st.n_groups * st.kchunks;
+          const uint8_t* src = p.wpack + st.w_off;
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&w_empty[stage], (round & 1) ^ 1);
+            mbar_arrive_expect_tx(&w_full[stage], st.chunk_bytes);
+            bulk_g2s(sW + stage * kStageBytes, src + static_cast<size_t>(c) * st.chunk_bytes, st.chunk_bytes,
+                     &w_full[stage]);
+            if (++stage == kNumStages) { stage = 0; ++round; }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, round = 0, gemm = 0;
+      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < p.n_steps; ++s) {
+          const StepDesc& st = p.steps[s];
+          if (st.n_groups == 0) continue;
+          mbar_wait(a_ready, gemm & 1);
+          tc_fence_after();
+          const uint32_t idesc = make_idesc_f16(kTileRows, st.ng, DT == DT_BF16, false, false);
+          const uint32_t b_lbo = static_cast<uint32_t>(st.ng) * 16;
+          for (int g = 0; g < st.n_groups; ++g) {
+            for (int kc = 0; kc < st.kchunks; ++kc) {
+              mbar_wait(&w_full[stage], round & 1);
+              tc_fence_after();
+              const uint32_t a_addr = sA_u + static_cast<uint32_t>(kc * st.k16 * 2) * kGranuleBytes;
+              const uint32_t b_addr = sW_u + stage * kStageBytes;
+              for (int k = 0; k < st.k16; ++k) {
+                const uint64_t da = make_smem_desc(a_addr + k * 2 * kGranuleBytes, kGranuleBytes, 128);
+                const uint64_t db = make_smem_desc(b_addr + k * 2 * b_lbo, b_lbo, 128);
+                umma_f16_ss(tmem_base + g * st.ng, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&w_empty[stage]);
+              if (++stage == kNumStages) { stage = 0; ++round; }
+            }
+          }
+          umma_commit(acc_full);
+          ++gemm;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    Epi e;
+    e.sA = smem_u32(sA);
+    const int q = warp & 3;
+    e.h = warp >> 2;
+    e.row = q * 32 + lane;
+    e.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    e.fval = 0.f;
+    e.fb = 0.f;
+    uint32_t gemm = 0;
+    const int nIt = p.H / 64;
+    const float beta = p.beta, inv_beta = p.inv_beta;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      e.tile = tile;
+      e.grow = static_cast<int64_t>(tile) * kTileRows + e.row;
+      e.valid = e.grow < p.n;
+      // ---------------------------------------------------------------- prologue: input block
+      const int first = p.steps[0].epi;
+      e.x[0] = e.x[1] = e.x[2] = 0.f;
+      if (first == EPI_FWD_HIDDEN) {
+        if (e.valid) {
+          if (p.src == SRC_POINTS) {
+            e.x[0] = __ldg(p.x + e.grow * 3 + 0);
+            e.x[1] = __ldg(p.x + e.grow * 3 + 1);
+            e.x[2] = __ldg(p.x + e.grow * 3 + 2);
+          } else if (p.src == SRC_GRID) {
+            // reference executor/executor.py:351-356: coords = stack(meshgrid(x,x,x,'ij'),-1).reshape(-1,3)
+            const int64_t idx = p.grid_off + e.grow;
+            const int64_t nn = p.grid_n;
+            const int iz = static_cast<int>(idx % nn);
+            const int iy = static_cast<int>((idx / nn) % nn);
+            const int ix = static_cast<int>(idx / (nn * nn));
+            e.x[0] = __ldg(p.axis + ix);
+            e.x[1] = __ldg(p.axis + iy);
+            e.x[2] = __ldg(p.axis + iz);
+          } else {
+            // octree cell centre from a 3x21-bit Morton key at the given level: c = -1 + (2 i + 1) * 2^-level
+            const uint64_t key = __ldg(p.keys + e.grow);
+            uint32_t ci[3] = {0, 0, 0};
+            for (int b = 0; b < p.level; ++b) {
+              ci[0] |= static_cast<uint32_t>((key >> (3 * b + 2)) & 1) << b;
+              ci[1] |= static_cast<uint32_t>((key >> (3 * b + 1)) & 1) << b;
+              ci[2] |= static_cast<uint32_t>((key >> (3 * b + 0)) & 1) << b;
+            }
+            const float hs = ldexpf(1.f, -p.level);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) e.x[j] = -1.f + (2.f * static_cast<float>(ci[j]) + 1.f) * hs;
+          }
+        }
+        const uint4 gx = xblock_granule<DT>(e.x, e.h, 1.f);
+        st_smem_v4(e.sA + e.h * kGranuleBytes + e.row * 16, gx);
+        if (p.flags & FL_SPILL_X)
+          *reinterpret_cast<uint4*>(p.Ximg + tile * static_cast<size_t>(2 * kGranuleBytes) + e.h * kGranuleBytes + e.row * 16) = gx;
+      } else {
+        // tangent / adjoint program: seeds
+        if (e.valid) {
+          e.fb = p.fbar ? __ldg(p.fbar + e.grow) : 0.f;
+          if (p.gbar) {
+            e.x[0] = __ldg(p.gbar + e.grow * 3 + 0);
+            e.x[1] = __ldg(p.gbar + e.grow * 3 + 1);
+            e.x[2] = __ldg(p.gbar + e.grow * 3 + 2);
+          }
+        } else {
+          e.fb = 0.f;
+        }
+        const uint4 gg = xblock_granule<DT>(e.x, e.h, 0.f);
+        st_smem_v4(e.sA + e.h * kGranuleBytes + e.row * 16, gg);
+        *reinterpret_cast<uint4*>(p.Gimg + tile * static_cast<size_t>(2 * kGranuleBytes) + e.h * kGranuleBytes + e.row * 16) = gg;
+        // f-bar block: cols 0-2 = fbar hi/lo/lolo, col 15 = 1
+        float fh, fl, fll;
+        split3<DT>(e.fb, fh, fl, fll);
+        float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (e.h == 0) { sv[0] = fh; sv[1] = fl; sv[2] = fll; } else { sv[7] = 1.f; }
+        *reinterpret_cast<uint4*>(p.Simg + tile * static_cast<size_t>(2 * kGranuleBytes) + e.h * kGranuleBytes + e.row * 16) = pack8<DT>(sv);
+      }
+      fence_proxy_async_smem();
+
+      for (int s = 0; s < p.n_steps; ++s) {
+        const StepDesc& st = p.steps[s];
+        if (st.n_groups != 0) {
+          tc_fence_before();
+          mbar_arrive(a_ready);
+          mbar_wait(acc_full, gemm & 1);
+          tc_fence_after();
+          ++gemm;
+        }
+        const int l = st.layer;
+        switch (st.epi) {
+          case EPI_FWD_HIDDEN: {
+            uint8_t* aimg = (p.flags & FL_SPILL_A) ? img_ptr(p.Aimg, l, p.n_tiles, tile, ib) : nullptr;
+            const bool inject = (p.skip > 0) && (l + 1 == p.skip);
+            for (int it = 0; it < nIt; ++it) {
+              const int c0 = it * 64 + e.h * 32;
+              float v[32], b[32];
+              load_vec32(p.bias + l * p.H + c0, b);
+              load_acc32(e, c0, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j] + b[j], beta, inv_beta, relu);
+              if (inject && c0 + 32 == p.H) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }
+              store_chunk<DT>(e, c0, v, aimg, true);
+            }
+            fence_proxy_async_smem();
+          } break;
+          case EPI_FWD_LAST: {
+            if (e.h == 0) {
+              uint32_t r[16];
+              tmem_ld16(e.taddr, r);
+              tmem_ld_wait();
+              float z = __uint_as_float(r[0]) + __ldg(p.bias + l * p.H);
+              // reference model/networks.py:104-105: tanh on the output when the activation is ReLU
+              e.fval = relu ? tanhf(z) : z;
+              if (e.valid && p.f_out) p.f_out[e.grow] = e.fval;
+            }
+          } break;
+          case EPI_REV_START: {
+            // q_{L-1} = w_L * act'(z_{L-1}); the A image still holds a_{L-1}
+            uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l, p.n_tiles, tile, ib) : nullptr;
+            for (int it = 0; it < nIt; ++it) {
+              const int c0 = it * 64 + e.h * 32;
+              float a[32], w[32];
+              load_vec32(p.w_last + c0, w);
+              load_chunk_smem<DT>(e, c0, a);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = w[j] * (1.f - act_em(a[j], beta, relu));
+              store_chunk<DT>(e, c0, a, qimg, true);
+            }
+            fence_proxy_async_smem();
+          } break;
+          case EPI_REV_HIDDEN: {
+            // GEMM r = q_l W_l done; q_{l-1} = r * act'(z_{l-1});  l = st.layer
+            const uint8_t* aimg = img_ptr(p.Aimg, l - 1, p.n_tiles, tile, ib);
+            uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l - 1, p.n_tiles, tile, ib) : nullptr;
+            const bool is_skip = (p.skip > 0) && (l == p.skip);
+            for (int it = 0; it < nIt; ++it) {
+              const int c0 = it * 64 + e.h * 32;
+              float v[32], a[32];
+              load_chunk_global<DT>(e, c0, aimg, a);
+              load_acc32(e, c0, v);
+              if (is_skip && c0 + 32 == p.H) {
+                // rows H-3..H-1 of W_skip multiply the raw input: their product is d f / d x through the skip
+                gskip[e.row * 3 + 0] = v[29]; gskip[e.row * 3 + 1] = v[30]; gskip[e.row * 3 + 2] = v[31];
+                v[29] = v[30] = v[31] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * (1.f - act_em(a[j], beta, relu));
+              store_chunk<DT>(e, c0, v, qimg, true);
+            }
+            fence_proxy_async_smem();
+          } break;
+          case EPI_REV_LAST: {
+            named_bar_sync(1, kEpiThreads);  // gskip written by the h=1 warps of an earlier step
+            if (e.h == 0) {
+              uint32_t r[16];
+              tmem_ld16(e.taddr, r);
+              tmem_ld_wait();
+              float g[3];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) g[j] = __uint_as_float(r[j]) + (p.skip > 0 ? gskip[e.row * 3 + j] : 0.f);
+              if (relu) {
+                const float d = 1.f - e.fval * e.fval;  // d tanh
+#pragma unroll
+                for (int j = 0; j < 3; ++j) g[j] *= d;
+              }
+              if (e.valid && p.g_out) {
+                p.g_out[e.grow * 3 + 0] = g[0]; p.g_out[e.grow * 3 + 1] = g[1]; p.g_out[e.grow * 3 + 2] = g[2];
+              }
+            }
+          } break;
+          case EPI_TAN_HIDDEN: {
+            // zdot_l in TMEM;  adot_l = s' zdot_l -> next A;  u_l = beta (1-s') q_l zdot_l
+            const uint8_t* aimg = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
+            const uint8_t* qimg = img_ptr(p.Qimg, l, p.n_tiles, tile, ib);
+            uint8_t* adimg = img_ptr(p.ADimg, l, p.n_tiles, tile, ib);
+            uint8_t* uimg = relu ? nullptr : img_ptr(p.Uimg, l, p.n_tiles, tile, ib);
+            const bool inject = (p.skip > 0) && (l + 1 == p.skip);
+            for (int it = 0; it < nIt; ++it) {
+              const int c0 = it * 64 + e.h * 32;
+              float zd[32], a[32];
+              load_chunk_global<DT>(e, c0, aimg, a);
+              load_acc32(e, c0, zd);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = act_em(a[j], beta, relu);  // a := 1 - s'
+              if (!relu) {
+                float qv[32];
+                load_chunk_global<DT>(e, c0, qimg, qv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) qv[j] = beta * a[j] * qv[j] * zd[j];
+                store_chunk<DT>(e, c0, qv, uimg, false);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) zd[j] = (1.f - a[j]) * zd[j];
+              if (inject && c0 + 32 == p.H) { zd[29] = e.x[0]; zd[30] = e.x[1]; zd[31] = e.x[2]; }
+              store_chunk<DT>(e, c0, zd, adimg, true);
+            }
+            fence_proxy_async_smem();
+          } break;
+          case EPI_ADJ_START: {
+            // Zbar_{L-1} = s' * (w_L fbar) + u_{L-1}
+            const uint8_t* aimg = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
+            const bool has_u = (p.flags & FL_TANGENT) && !relu;
+            const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
+            uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
+            for (int it = 0; it < nIt; ++it) {
+              const int c0 = it * 64 + e.h * 32;
+              float a[32], w[32];
+              load_vec32(p.w_last + c0, w);
+              load_chunk_global<DT>(e, c0, aimg, a);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = (1.f - act_em(a[j], beta, relu)) * (w[j] * e.fb);
+              if (has_u) {
+                float u[32];
+                load_chunk_global<DT>(e, c0, uimg, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] += u[j];
+              }
+              store_chunk<DT>(e, c0, a, zimg, true);
+            }
+            fence_proxy_async_smem();
+          } break;
+          case EPI_ADJ_HIDDEN: {
+            // GEMM abar = Zbar_{l+1} W_{l+1} done;  Zbar_l = s' abar + u_l
+            const uint8_t* aimg = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
+            const bool has_u = (p.flags & FL_TANGENT) && !relu;
+            const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
+            uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
+            const bool from_skip = (p.skip > 0) && (l + 1 == p.skip);
+            for (int it = 0; it < nIt; ++it) {
+              const int c0 = it * 64 + e.h * 32;
+              float v[32], a[32];
+              load_chunk_global<DT>(e, c0, aimg, a);
+              load_acc32(e, c0, v);
+              if (from_skip && c0 + 32 == p.H) v[29] = v[30] = v[31] = 0.f;  // those rows fed the raw input
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (1.f - act_em(a[j], beta, relu)) * v[j];
+              if (has_u) {
+                float u[32];
+                load_chunk_global<DT>(e, c0, uimg, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += u[j];
+              }
+              store_chunk<DT>(e, c0, v, zimg, true);
+            }
+            fence_proxy_async_smem();
+          } break;
+          default: break;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_chain(const ChainParams& p, int dtype, int num_sms, cudaStream_t stream) {
+  static bool attr_set[2] = {false, false};
+  auto kfn = dtype == DT_BF16 ? chain_kernel<DT_BF16> : chain_kernel<DT_FP16>;
+  if (!attr_set[dtype]) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kChainSmem));
+    if (e != cudaSuccess) return e;
+    attr_set[dtype] = true;
+  }
+  if (p.n_tiles <= 0) return cudaSuccess;
+  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  kfn<<<grid, kChainThreads, kChainSmem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace sdf

@@ -1,0 +1,113 @@
+// Internal definitions shared by the kernels (chain.cu, dw.cu, aux.cu) and the C-ABI (api.cu).
+//
+// Data layout ("granule-major operand image"), used for every 16-bit matrix this library keeps in shared
+// memory or spills to HBM:  a [R rows x C cols] matrix is stored as [C/8 granules][R rows][8 elements],
+// i.e. element (r, c) lives at byte ((c/8)*R + r)*16 + (c%8)*2.  With R = 128 this single image is
+//   * a legal no-swizzle K-major  UMMA operand (rows = points,  K = features)  -> the layer chain,
+//   * a legal no-swizzle MN-major UMMA operand (K = points, MN = features)     -> the weight-gradient GEMM,
+//   * perfectly coalesced for epilogue threads (lane = row: 32 lanes x 16 B contiguous),
+//   * movable with one 1-D bulk copy per contiguous granule range.
+#pragma once
+#include <cstdint>
+
+namespace sdf {
+
+constexpr int kTileRows = 128;           // rows of one operand image (points per tile; 64 hi + 64 lo when split)
+constexpr int kGranuleBytes = kTileRows * 16;  // 2048: one 8-column granule of a tile image
+constexpr int kMaxH = 512;
+constexpr int kMaxLayers = 16;           // hidden layers
+constexpr int kMaxSteps = 2 * kMaxLayers + 4;
+constexpr int kStageBytes = 32768;       // one weight chunk (<= 256 rows x 64 K x 2 B)
+constexpr int kXCols = 16;               // width of the input block (x / g-bar / f-bar split columns)
+
+// element type of the 16-bit operands
+enum : int { DT_BF16 = 0, DT_FP16 = 1 };
+
+// epilogue kinds of the layer chain
+enum : int {
+  EPI_FWD_HIDDEN = 0,  // a = act(z + b)                         -> next A operand (+ spill A)
+  EPI_FWD_LAST = 1,    // f = z_L + b_L (tanh in relu mode)      -> f_out
+  EPI_REV_START = 2,   // q_{L-1} = w_L * act'(z_{L-1})          (no GEMM)
+  EPI_REV_HIDDEN = 3,  // q_{l-1} = (q_l W_l) * act'(z_{l-1})    (+ skip rows -> g, spill Q)
+  EPI_REV_LAST = 4,    // g = q_0 W_0 (+ skip part)              -> g_out
+  EPI_TAN_HIDDEN = 5,  // adot_l = act'(z_l) * zdot_l ; u_l = act''(z_l) s_l zdot_l   (spill AD, U)
+  EPI_ADJ_START = 6,   // Zbar_{L-1} = act'(z_{L-1}) w_L fbar + u_{L-1}               (no GEMM)
+  EPI_ADJ_HIDDEN = 7,  // Zbar_l = act'(z_l) (Zbar_{l+1} W_{l+1}) + u_l               (spill Z)
+};
+
+struct StepDesc {
+  int32_t epi;
+  int32_t layer;        // meaning depends on epi (index of the layer whose activation state is touched)
+  int32_t n_groups;     // TMEM column groups of this GEMM; 0 = element-wise step without GEMM
+  int32_t ng;           // N (rows of the weight chunk) per group
+  int32_t kchunks;      // weight chunks per group
+  int32_t k16;          // K=16 instructions per chunk
+  uint32_t chunk_bytes;
+  uint32_t w_off;       // byte offset of the first chunk of this step in the packed weight stream
+};
+
+// where the points of a tile come from
+enum : int { SRC_POINTS = 0, SRC_GRID = 1, SRC_OCTREE = 2 };
+
+// flag bits
+enum : uint32_t {
+  FL_SPILL_A = 1u << 0,   // forward sweep writes the activation images (needed by reverse / training)
+  FL_SPILL_Q = 1u << 1,   // reverse sweep writes q images (training)
+  FL_SPILL_X = 1u << 2,   // write the input-block image (training, for dW_0 / biases)
+  FL_TANGENT = 1u << 3,   // TA kernel: run the tangent sweep (second-order terms present)
+  FL_RELU = 1u << 4,      // ReLU hidden activation + tanh output (beta == 0 in the reference ini)
+};
+
+struct ChainParams {
+  // network
+  int32_t H, L, skip, n_steps;
+  float beta, inv_beta;
+  const float* bias;       // [(L+1)][H] fp32, zero padded
+  const float* w_last;     // [H] fp32 (last layer weight row)
+  const uint8_t* wpack;    // packed 16-bit weight chunk stream
+  StepDesc steps[kMaxSteps];
+  // points
+  int64_t n;               // valid points
+  int32_t n_tiles;
+  int32_t src;
+  const float* x;          // SRC_POINTS: [n][3]
+  const float* axis;       // SRC_GRID: [grid_n] axis vector (torch.linspace output)
+  int32_t grid_n;
+  int64_t grid_off;        // flat index of the first point ((ix*n + iy)*n + iz ordering)
+  const uint64_t* keys;    // SRC_OCTREE: Morton keys of the cells of one level
+  int32_t level;
+  // outputs
+  float* f_out;            // [n]
+  float* g_out;            // [n][3]
+  // seeds (TA kernel)
+  const float* fbar;       // [n]
+  const float* gbar;       // [n][3]
+  // spill images, each [layer][tile][image]
+  uint8_t* Aimg;
+  uint8_t* Qimg;
+  uint8_t* ADimg;
+  uint8_t* Uimg;
+  uint8_t* Zimg;
+  uint8_t* Ximg;           // [tile][2 granules]  x split block (+ ones column)
+  uint8_t* Gimg;           // [tile][2 granules]  g-bar split block
+  uint8_t* Simg;           // [tile][2 granules]  f-bar split block (+ ones column)
+  uint32_t flags;
+};
+
+// one unit of work of the weight-gradient kernel:  out[n][m] += sum_tiles  A1^T B1 (+ A2^T B2)
+struct DwItem {
+  const uint8_t* A1;
+  const uint8_t* B1;
+  const uint8_t* A2;       // nullptr: single term
+  const uint8_t* B2;
+  uint32_t a_tstride, b_tstride;   // bytes between consecutive tiles of the A / B images
+  uint32_t a_off, b_off;           // byte offset of the first granule used inside a tile image
+  uint32_t n;                      // 256 or 16
+  uint32_t tile0, tile1;
+  uint32_t out_ld;                 // leading dimension (elements) of out (index [n][m])
+  float* out;
+};
+
+__host__ __device__ inline uint32_t img_bytes(int H) { return static_cast<uint32_t>(H / 8) * kGranuleBytes; }
+
+}  // namespace sdf

@@ -1,0 +1,260 @@
+"""Per-device engine: owns one ``sdfnet_t`` handle of libsdfnet.so and the scratch buffers its calls need.
+
+This is plumbing only: PyTorch supplies device memory and the CUDA stream, every computation happens in the
+hand-written sm_100a kernels behind the C ABI of ``include/sdfnet.h``.  There is no CPU or eager-PyTorch fallback:
+non-CUDA tensors raise.
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from . import _lib
+
+DTYPE_IDS = {"bf16": 0, "fp16": 1}
+PRECISION_IDS = {"fast": 0, "parity": 1}
+
+# default cap of the spill workspace of one training chunk (bytes); SDFNET_WS_GB overrides
+_WS_CAP_BYTES = int(float(os.environ.get("SDFNET_WS_GB", "24")) * (1 << 30))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_points(x, cols, name):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the SDF hot path has no CPU fallback")
+    if x.dim() != 2 or x.shape[1] != cols:
+        raise RuntimeError(f"{name} must have shape [N, {cols}] (got {tuple(x.shape)})")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32 (got {x.dtype})")
+    return x.detach().contiguous()
+
+
+class Engine:
+    """One network description bound to one CUDA device."""
+
+    def __init__(self, hidden, num_hidden, skip_layer, beta, device, dtype="fp16", precision="fast", d_in=3):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("sdfnet engines exist on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        desc = _lib.SdfnetDesc(
+            d_in=int(d_in),
+            hidden=int(hidden),
+            num_hidden=int(num_hidden),
+            skip_layer=int(skip_layer),
+            beta=float(beta),
+            dtype=DTYPE_IDS[dtype],
+            precision=PRECISION_IDS[precision],
+            device=self.device.index,
+        )
+        self.hidden, self.num_hidden, self.skip_layer, self.beta = int(hidden), int(num_hidden), int(skip_layer), float(beta)
+        self.dtype, self.precision = dtype, precision
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_create(ctypes.byref(desc), ctypes.byref(h)), "sdfnet_create")
+        self.handle = h
+        self.num_params = int(self.lib.sdfnet_num_params(self.handle))
+        self._ws = None
+        self._packed_key = None
+        self.launches = 0  # kernels launched through this engine (bench.py reports it as gpu_launches)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.sdfnet_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def pack(self, weights, biases, key=None):
+        """Re-pack lin{i}.weight / lin{i}.bias into the UMMA operand images (skipped if ``key`` is unchanged)."""
+        if key is not None and key == self._packed_key:
+            return
+        n = self.num_hidden + 1
+        if len(weights) != n or len(biases) != n:
+            raise RuntimeError(f"expected {n} weight and bias tensors")
+        keep = []
+        wp = (ctypes.c_void_p * n)()
+        bp = (ctypes.c_void_p * n)()
+        for i, (w, b) in enumerate(zip(weights, biases)):
+            for t in (w, b):
+                if not t.is_cuda or t.device != self.device or t.dtype != torch.float32:
+                    raise RuntimeError("parameters must be float32 CUDA tensors on the engine's device (no CPU fallback)")
+            w = w.detach().contiguous()
+            b = b.detach().contiguous()
+            keep += [w, b]
+            wp[i] = w.data_ptr()
+            bp[i] = b.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_pack_weights(self.handle, wp, bp, _stream(self.device)), "sdfnet_pack_weights")
+        self.launches += 2 * n + (n - 1) + 1
+        self._packed_key = key
+
+    # ------------------------------------------------------------------ scratch
+    def workspace(self, n_points, mode):
+        need = int(self.lib.sdfnet_workspace_bytes(self.handle, int(n_points), int(mode)))
+        need = min(need, _WS_CAP_BYTES)
+        per_tile = int(self.lib.sdfnet_workspace_bytes(self.handle, 128, int(mode)))
+        need = max(need, per_tile + 4096)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _chunks(self, n, mode):
+        per_tile = int(self.lib.sdfnet_workspace_bytes(self.handle, 128, int(mode))) - 1024
+        cap_tiles = max(1, (self._ws.numel() - 1024) // per_tile)
+        pts = cap_tiles * 128
+        return max(1, math.ceil(n / pts))
+
+    # ------------------------------------------------------------------ inference
+    def forward(self, x):
+        x = _check_points(x, 3, "points")
+        n = x.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+        if n:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.sdfnet_forward(self.handle, _ptr(x), n, _ptr(out), _stream(self.device)), "sdfnet_forward")
+            self.launches += 1
+        return out
+
+    def forward_grad(self, x):
+        x = _check_points(x, 3, "points")
+        n = x.shape[0]
+        f = torch.empty(n, dtype=torch.float32, device=x.device)
+        g = torch.empty(n, 3, dtype=torch.float32, device=x.device)
+        if n:
+            ws = self.workspace(n, 0)
+            with torch.cuda.device(self.device):
+                _lib.check(
+                    self.lib.sdfnet_forward_grad(self.handle, _ptr(x), n, _ptr(f), _ptr(g), _ptr(ws), ws.numel(), _stream(self.device)),
+                    "sdfnet_forward_grad",
+                )
+            self.launches += self._chunks(n, 0)
+        return f, g
+
+    def grid_eval(self, axis, first, count, out=None):
+        if not axis.is_cuda or axis.dtype != torch.float32 or axis.dim() != 1:
+            raise RuntimeError("axis must be a 1-D float32 CUDA tensor (no CPU fallback)")
+        axis = axis.contiguous()
+        if out is None:
+            out = torch.empty(int(count), dtype=torch.float32, device=axis.device)
+        elif out.numel() < count or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError("grid_eval: output buffer too small or not contiguous float32")
+        if count:
+            with torch.cuda.device(self.device):
+                _lib.check(
+                    self.lib.sdfnet_grid_eval(self.handle, _ptr(axis), int(axis.numel()), int(first), int(count), _ptr(out), _stream(self.device)),
+                    "sdfnet_grid_eval",
+                )
+            self.launches += math.ceil(count / (1 << 30))
+        return out
+
+    def octree_level(self, keys, level, band, want_flags=True):
+        if not keys.is_cuda or keys.dtype not in (torch.int64, torch.uint64):
+            raise RuntimeError("keys must be an int64 CUDA tensor of Morton codes (no CPU fallback)")
+        keys = keys.contiguous()
+        n = keys.numel()
+        sdf = torch.empty(n, dtype=torch.float32, device=keys.device)
+        flags = torch.empty(n, dtype=torch.uint8, device=keys.device) if want_flags else None
+        if n:
+            with torch.cuda.device(self.device):
+                _lib.check(
+                    self.lib.sdfnet_octree_level(self.handle, _ptr(keys), n, int(level), float(band), _ptr(sdf), _ptr(flags), _stream(self.device)),
+                    "sdfnet_octree_level",
+                )
+            self.launches += 2 if want_flags else 1
+        return sdf, flags
+
+    # ------------------------------------------------------------------ gradients
+    def zero_grads(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_zero_grads(self.handle, _stream(self.device)), "sdfnet_zero_grads")
+
+    def read_grads(self, out=None, scale=1.0):
+        if out is None:
+            out = torch.empty(self.num_params, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_read_grads(self.handle, _ptr(out), float(scale), _stream(self.device)), "sdfnet_read_grads")
+        self.launches += 1
+        return out
+
+    def backward(self, x, fbar=None, gbar=None):
+        """Accumulate dL/dparams for seeds fbar = dL/df [N] and gbar = dL/d(grad_x f) [N,3]."""
+        x = _check_points(x, 3, "points")
+        n = x.shape[0]
+        if n == 0 or (fbar is None and gbar is None):
+            return
+        if fbar is not None:
+            fbar = fbar.detach().reshape(-1).to(torch.float32).contiguous()
+            if fbar.numel() != n:
+                raise RuntimeError("fbar must have one entry per point")
+        if gbar is not None:
+            gbar = _check_points(gbar, 3, "gbar")
+            if gbar.shape[0] != n:
+                raise RuntimeError("gbar must have one row per point")
+        ws = self.workspace(n, 1)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.sdfnet_backward(self.handle, _ptr(x), n, _ptr(fbar), _ptr(gbar), _ptr(ws), ws.numel(), _stream(self.device)),
+                "sdfnet_backward",
+            )
+        self.launches += 4 * self._chunks(n, 1)
+
+    def train_step_igr(self, x, y, cfg, loss_sums):
+        x = _check_points(x, 3, "x_batch")
+        y = _check_points(y, 4, "y_batch")
+        if y.shape[0] != x.shape[0]:
+            raise RuntimeError("x_batch and y_batch must have the same number of rows")
+        n = x.shape[0]
+        if n == 0:
+            return
+        ws = self.workspace(n, 1)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.sdfnet_train_step_igr(
+                    self.handle, _ptr(x), _ptr(y), n, ctypes.byref(cfg), _ptr(loss_sums), _ptr(ws), ws.numel(), _stream(self.device)
+                ),
+                "sdfnet_train_step_igr",
+            )
+        self.launches += 5 * self._chunks(n, 1)
+
+    def train_step_pcd(self, x, n_global, xp, m_global, lambda_g, loss_sums):
+        x = _check_points(x, 3, "surface points")
+        xp = _check_points(xp, 3, "perturbed points")
+        n, m = x.shape[0], xp.shape[0]
+        ws = self.workspace(max(n, m, 1), 1)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.sdfnet_train_step_pcd(
+                    self.handle, _ptr(x), n, int(n_global), _ptr(xp), m, int(m_global), float(lambda_g), _ptr(loss_sums), _ptr(ws),
+                    ws.numel(), _stream(self.device),
+                ),
+                "sdfnet_train_step_pcd",
+            )
+        self.launches += 5 * (self._chunks(max(n, 1), 1) + self._chunks(max(m, 1), 1))
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam(lr).step() on a flat fp32 parameter vector (executor/executor.py:160,177)."""
+    lib = _lib.load()
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("adam_step operates on contiguous float32 CUDA tensors (no CPU fallback)")
+    with torch.cuda.device(params.device):
+        _lib.check(
+            lib.sdfnet_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), float(lr), float(beta1),
+                                 float(beta2), float(eps), int(step), _stream(params.device)),
+            "sdfnet_adam_step",
+        )

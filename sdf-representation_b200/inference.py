@@ -1,0 +1,126 @@
+"""Dense-grid and octree SDF inference (reference ``executor/executor.py:346-400``,
+``evaluations/post_process.py:40-88``, ``evaluations/compare_octree_dl.py:20-36``) on the fused forward kernel.
+
+Grid: the reference materialises ``stack(meshgrid(x, x, x, 'ij'), -1).reshape(-1, 3)`` (12.9 GB at 1024^3) and
+loops over ``postprocessbatchsize`` slices.  Here the kernel indexes the n-element axis vector produced by the same
+``torch.linspace(-1, 1, n)`` call (bit-identical coordinates) and writes the ``[ix, iy, iz]`` block
+directly.  Multi-GPU: slabs of the slowest axis (ix), no collective.
+
+Octree (build-defined, SURVEY.md T6 -- the reference has no refinement rule): root [-1,1]^3, uniform to
+``refine_lvl_uni``, then a cell is refined iff ``|f(centre)| <= band * h_level`` (h_level = 2 / 2^level), up to
+``max_level``; cells are 3-bit-per-level Morton keys (x bit highest).  Subtrees shard across ranks, no collective.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from . import distributed as _dist
+from .engine import _ptr, _stream
+
+SQRT3_2 = math.sqrt(3.0) / 2.0
+
+
+def grid_axis(n, device):
+    """The coordinate vector the reference uses (executor/executor.py:351)."""
+    return torch.linspace(-1, 1, n, device=device)
+
+
+@torch.no_grad()
+def grid_sdf(model, n, ix0=0, ix1=None, out=None):
+    """SDF on planes [ix0, ix1) of the n^3 grid -> float32 CUDA tensor [ix1-ix0, n, n] (index [ix, iy, iz])."""
+    from .losses import _unwrap
+
+    net = _unwrap(model)
+    eng = net.engine()
+    ix1 = n if ix1 is None else ix1
+    if not (0 <= ix0 <= ix1 <= n):
+        raise ValueError(f"slab [{ix0}, {ix1}) outside [0, {n}]")
+    axis = grid_axis(n, eng.device)
+    count = (ix1 - ix0) * n * n
+    flat = eng.grid_eval(axis, ix0 * n * n, count, out=None if out is None else out.view(-1))
+    return flat.view(ix1 - ix0, n, n)
+
+
+@torch.no_grad()
+def grid_sdf_sharded(model, n, halo=0):
+    """This rank's slab of the n^3 grid (plus ``halo`` extra planes so it can classify its own boundary cells).
+    Returns (ix0, ix1, sdf[ix0:ix1+halo])."""
+    ix0, ix1 = _dist.slab_bounds(n)
+    hi = min(n, ix1 + halo)
+    return ix0, ix1, grid_sdf(model, n, ix0, hi)
+
+
+@torch.no_grad()
+def reconstruct_grid(model, cubesize, ppbatchsize=None):
+    """Drop-in for the grid loop of executor/executor.py:374-387: returns the [n,n,n] float32 volume on the device.
+    ``ppbatchsize`` is accepted for interface compatibility; the persistent kernel needs no host-side batching."""
+    return grid_sdf(model, cubesize, 0, cubesize)
+
+
+# ---------------------------------------------------------------------------------------------- marching cubes
+@torch.no_grad()
+def mc_classify(sdf_block, compact=True):
+    """Cell classification of ``skimage.measure.marching_cubes(level=0)`` (executor/executor.py:388) on a block
+    [nx, ny, nz]: returns (case_index uint8 [(nx-1),(ny-1),(nz-1)], active flat cell indices int64 | None)."""
+    lib = _lib.load()
+    if not sdf_block.is_cuda or sdf_block.dtype != torch.float32 or sdf_block.dim() != 3:
+        raise RuntimeError("mc_classify needs a float32 CUDA block [nx, ny, nz] (no CPU fallback)")
+    sdf_block = sdf_block.contiguous()
+    nx, ny, nz = sdf_block.shape
+    dev = sdf_block.device
+    cases = torch.empty((nx - 1, ny - 1, nz - 1), dtype=torch.uint8, device=dev)
+    active = n_active = None
+    if compact:
+        active = torch.empty(cases.numel(), dtype=torch.int64, device=dev)
+        n_active = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfnet_mc_classify(_ptr(sdf_block), nx, ny, nz, _ptr(cases), _ptr(active), _ptr(n_active), _stream(dev)),
+                   "sdfnet_mc_classify")
+    if compact:
+        active = active[: int(n_active.item())]
+    return cases, active
+
+
+# ---------------------------------------------------------------------------------------------- octree
+def octree_children(keys, flags):
+    """Morton keys of the 8 children of every flagged cell, in order (device-side ordered compaction)."""
+    lib = _lib.load()
+    dev = keys.device
+    n = keys.numel()
+    out = torch.empty(8 * n, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            _lib.check(lib.sdfnet_octree_refine(_ptr(keys), _ptr(flags), n, _ptr(out), _ptr(cnt), _stream(dev)), "sdfnet_octree_refine")
+    return out[: 8 * int(cnt.item())]
+
+
+@torch.no_grad()
+def octree_build(model, max_level=10, refine_lvl_uni=3, band=SQRT3_2, rank=None, world=None):
+    """Adaptive octree of the zero level set down to ``max_level``.  Returns a list with one dict per level:
+    {level, keys, sdf, flags}.  With world > 1 each rank refines only the subtrees (cells of level
+    ``refine_lvl_uni``) dealt to it round-robin; there is no collective."""
+    from .losses import _unwrap
+
+    net = _unwrap(model)
+    eng = net.engine()
+    dev = eng.device
+    world = _dist.world_size() if world is None else world
+    rank = _dist.rank() if rank is None else rank
+    levels = []
+    keys = torch.zeros(1, dtype=torch.int64, device=dev)
+    for level in range(0, max_level + 1):
+        if level == refine_lvl_uni and world > 1:
+            keys = keys[(torch.arange(keys.numel(), device=dev) % world) == rank]
+        sdf, flags = eng.octree_level(keys, level, band, want_flags=True)
+        if level < refine_lvl_uni:
+            flags = torch.ones_like(flags)  # uniform refinement below refine_lvl_uni
+        levels.append({"level": level, "keys": keys, "sdf": sdf, "flags": flags})
+        if level == max_level:
+            break
+        keys = octree_children(keys, flags)
+        if keys.numel() == 0:
+            break
+    return levels

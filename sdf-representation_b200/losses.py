@@ -1,0 +1,183 @@
+"""Drop-ins for the loss callables of the reference's ``model/losses.py`` that sit on the hot path.
+
+Protocol (reference ``model/losses.py:5``): ``loss(x_batch, y_batch, model, epoch) -> scalar`` with ``__name__()``
+and, for IGRLOSS, the attribute ``lambda_g`` (read by ``executor/executordistributed.py:26``).
+
+``IGRLOSS`` recognises the drop-in ``ImplicitNet`` and runs ONE fused training step in the CUDA library
+(forward, input gradient, loss seeds + warp-shuffle loss reductions, tangent / adjoint sweeps, weight-gradient
+GEMMs); the returned scalar carries a graph whose backward only hands the already computed parameter gradients to
+autograd, so ``loss.backward(); optimizer.step()`` of ``executor/executor.py:174-177`` works unchanged.
+
+Data term: the reference subtracts a ``[N]`` label from a ``[N,1]`` prediction, which broadcasts to
+``[N,N]``; ``data_term="pairwise"`` (default) reproduces exactly that mean over all pairs in O(N) with moment sums,
+``data_term="pointwise"`` is the per-point loss the authors presumably meant.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .networks import ImplicitNet, _split_flat
+from . import distributed as _dist
+
+
+def _unwrap(model):
+    m = model.module if isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel)) else model
+    if not isinstance(m, ImplicitNet):
+        raise TypeError(
+            "sdf-representation_b200 losses drive the fused CUDA path of the drop-in ImplicitNet; got "
+            f"{type(m).__name__}.  There is no generic eager fallback."
+        )
+    return m
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss value + precomputed flat parameter gradient -> a scalar whose backward scatters those gradients."""
+
+    @staticmethod
+    def forward(ctx, loss_value, flat_grads, *params):
+        ctx.save_for_backward(flat_grads)
+        ctx.params = params
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        (flat,) = ctx.saved_tensors
+        gp = [g * gout for g in _split_flat(flat, ctx.params)]
+        return (None, None, *gp)
+
+
+def compute_normal(model, pj):
+    """grad_x f(pj), differentiable w.r.t. the weights (reference model/losses.py:283-296)."""
+    net = _unwrap(model)
+    pj.requires_grad = True  # the reference flips this in place (model/losses.py:285)
+    return net.input_gradient(pj)[:, -3:]
+
+
+def gradient(inputs, outputs):
+    """reference executor/executordistributed.py:10-19 (generic autograd path through the drop-in module)."""
+    d_points = torch.ones_like(outputs, requires_grad=False, device=outputs.device)
+    return torch.autograd.grad(outputs=outputs, inputs=inputs, grad_outputs=d_points, create_graph=True, retain_graph=True,
+                               only_inputs=True)[0][:, -3:]
+
+
+class IGRLOSS(nn.Module):
+    """reference model/losses.py:96-137"""
+
+    def __init__(self, delta=0.1, tau=1, lambda_g=0.1, regularizer_threshold=1, data_term="pairwise"):
+        super().__init__()
+        self.delta = delta
+        self.tau = tau
+        self.lambda_g = lambda_g
+        self.regularizer_threshold = regularizer_threshold
+        if data_term not in ("pairwise", "pointwise"):
+            raise ValueError("data_term must be 'pairwise' (reference-exact) or 'pointwise'")
+        self.data_term = data_term
+        self.last_terms = None  # (data, reg, eik) device tensor of the last call, for logging
+
+    def __name__(self):
+        return "IGRLOSS"
+
+    def forward(self, x_batch, y_batch, model, epoch):
+        net = _unwrap(model)
+        eng = net._engine_for(x_batch)
+        dev = x_batch.device
+        n = x_batch.shape[0]
+        world = _dist.world_size()
+        n_global = n * world
+        # global mean of the clamped labels (needed before the seeds exist in pairwise mode)
+        t_sum = y_batch[:, 0].detach().clamp(-self.delta, self.delta).sum(dtype=torch.float64).reshape(1)
+        _dist.all_reduce_sum(t_sum)
+        mean_t = (t_sum / n_global).to(torch.float32)
+        cfg = _lib.SdfnetIgrCfg(
+            delta=float(self.delta), tau=float(self.tau), lambda_g=float(self.lambda_g),
+            regularizer_threshold=float(self.regularizer_threshold),
+            data_term=0 if self.data_term == "pairwise" else 1, mean_t=0.0, n_global=int(n_global),
+            mean_t_dev=ctypes.c_void_p(mean_t.data_ptr()),
+        )
+        sums = torch.zeros(8, dtype=torch.float64, device=dev)
+        eng.zero_grads()
+        eng.train_step_igr(x_batch, y_batch, cfg, sums)
+        flat = eng.read_grads()
+        if world > 1:
+            # one fp32 sum-allreduce of the whole gradient vector + one 8-double message with the loss sums
+            _dist.all_reduce_sum(flat)
+            _dist.all_reduce_sum(sums)
+        N = float(n_global)
+        if self.data_term == "pairwise":
+            data = sums[1] / N + sums[3] / N - 2.0 * (sums[0] / N) * (sums[2] / N)
+        else:
+            data = sums[4] / N
+        reg = sums[5] / N
+        eik = sums[6] / N
+        self.last_terms = torch.stack([data, reg, eik]).detach()
+        value = (data + self.tau * reg + self.lambda_g * eik).to(torch.float32)
+        return _FusedLoss.apply(value, flat, *net._ordered_params())
+
+
+class WeightedSmoothL2Loss(nn.Module):
+    """reference model/losses.py:50-69 (the loss the shipped ini selects).  First order only: network forward and
+    backward run in the CUDA library, the [N]-vector loss arithmetic is closed-form moments of the reference's
+    [N,N] broadcast (pairwise) or the per-point form."""
+
+    def __init__(self, weight_factor=0.5, delta=0.1, data_term="pairwise"):
+        super().__init__()
+        self.weight_factor = weight_factor
+        self.delta = delta
+        if data_term not in ("pairwise", "pointwise"):
+            raise ValueError("data_term must be 'pairwise' (reference-exact) or 'pointwise'")
+        self.data_term = data_term
+
+    def __name__(self):
+        return "WeightedSmoothL2Loss"
+
+    def forward(self, x_batch, y_batch, model, epoch):
+        _unwrap(model)
+        t = torch.clamp(y_batch[:, 0], -self.delta, self.delta)
+        p = torch.clamp(model(x_batch), -self.delta, self.delta)[:, 0]
+        w = 1.0 + self.weight_factor * torch.exp(-torch.abs(t))
+        if self.data_term == "pairwise":
+            # mean_{i,j} w_j (t_j - p_i)^2
+            return (w * t * t).mean() - 2.0 * p.mean() * (w * t).mean() + (p * p).mean() * w.mean()
+        return (w * (t - p) ** 2).mean()
+
+
+def get_points(pc_input, local_sigma=0.0001, generator=None):
+    """reference executor/executordistributed.py:108-123: a random third of the batch, perturbed by N(0, sigma^2)."""
+    sample_size = pc_input.shape[0]
+    perm = torch.randperm(sample_size, generator=generator)[: sample_size // 3]
+    sample = pc_input[perm.to(pc_input.device)]
+    noise = torch.randn(sample.shape, generator=generator, dtype=sample.dtype).to(pc_input.device)
+    return sample + noise * local_sigma
+
+
+class PointCloudLoss(nn.Module):
+    """The loss of the reference's point-cloud ("distributed") executor, executor/executordistributed.py:63-79:
+    ``mean |f(x)| + lambda_g * mean((|grad f(x~)| - 1)^2)``, fused like IGRLOSS."""
+
+    def __init__(self, lambda_g=0.1):
+        super().__init__()
+        self.lambda_g = lambda_g
+        self.last_terms = None
+
+    def __name__(self):
+        return "PointCloudLoss"
+
+    def forward(self, x_batch, sampled_pts, model, epoch=0):
+        net = _unwrap(model)
+        eng = net._engine_for(x_batch)
+        world = _dist.world_size()
+        n, m = x_batch.shape[0], sampled_pts.shape[0]
+        sums = torch.zeros(8, dtype=torch.float64, device=x_batch.device)
+        eng.zero_grads()
+        eng.train_step_pcd(x_batch, n * world, sampled_pts, m * world, self.lambda_g, sums)
+        flat = eng.read_grads()
+        if world > 1:
+            _dist.all_reduce_sum(flat)
+            _dist.all_reduce_sum(sums)
+        surf = sums[0] / float(n * world)
+        eik = sums[1] / float(max(m * world, 1))
+        self.last_terms = torch.stack([surf, eik]).detach()
+        value = (surf + self.lambda_g * eik).to(torch.float32)
+        return _FusedLoss.apply(value, flat, *net._ordered_params())

@@ -1,0 +1,368 @@
+"""GPU parity tests proper: the CUDA path (through the ctypes C-ABI binding) against the oracle and against the golden
+vectors produced by the unmodified reference.  Run on the B200 box: pytest -m gpu."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sdf_oracle as orc
+from helpers import golden_grads, golden_params, load_golden, rel_err, skip_of
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances.  Box diagonal of [-1,1]^3 is 2*sqrt(3); the north star's fp32/TF32-mode bound is 1e-4 of it.
+TOL_PARITY = 1e-4 * 2 * math.sqrt(3)          # 3.46e-4 absolute on f and on each component of grad_x f
+TOL_FAST_F = 5e-3                              # single-pass fp16 operands, fp32 accumulate (looser, stated separately)
+TOL_FAST_G = 2e-2
+TOL_GRAD_REL = {"fast": 3e-2, "parity": 2e-3}  # relative L2 error of each parameter-gradient tensor
+MODES = ["fast", "parity"]
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def make_net(d, precision, dtype="fp16"):
+    import sdf_representation_b200 as pkg
+
+    L, H = int(d["num_hidden"]), int(d["hidden"])
+    beta = float(d["beta"])
+    net = pkg.ImplicitNet(3, [H] * L, skip_of(d), beta, True, precision=precision, dtype=dtype)
+    sd = {}
+    for i in range(L + 1):
+        sd[f"lin{i}.weight"] = torch.from_numpy(d[f"lin{i}_weight"])
+        sd[f"lin{i}.bias"] = torch.from_numpy(d[f"lin{i}_bias"])
+    net.load_state_dict(sd)
+    return net.to(dev())
+
+
+def tol_f(mode):
+    return TOL_PARITY if mode == "parity" else TOL_FAST_F
+
+
+def tol_g(mode):
+    return TOL_PARITY if mode == "parity" else TOL_FAST_G
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["softplus_skip_128x4.npz", "relu_tanh_128x3.npz"])
+def test_forward_matches_reference(name, mode):
+    d = load_golden(name)
+    net = make_net(d, mode)
+    x = torch.from_numpy(d["x"]).to(dev())
+    with torch.no_grad():
+        f = net(x)
+    assert f.shape == (x.shape[0], 1)
+    err = np.abs(f[:, 0].cpu().numpy() - d["f"]).max()
+    print(f"{name} {mode}: max|f - ref| = {err:.3e}")
+    assert err < tol_f(mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["softplus_skip_128x4.npz", "relu_tanh_128x3.npz"])
+def test_input_gradient_matches_reference(name, mode):
+    d = load_golden(name)
+    net = make_net(d, mode)
+    x = torch.from_numpy(d["x"]).to(dev())
+    f, g = net.sdf_and_gradient(x)
+    ef = np.abs(f[:, 0].cpu().numpy() - d["f"]).max()
+    eg = np.abs(g.cpu().numpy() - d["g"]).max()
+    print(f"{name} {mode}: max|f - ref| = {ef:.3e}  max|g - ref| = {eg:.3e}")
+    assert ef < tol_f(mode) and eg < tol_g(mode)
+
+
+def _check_grads(net, d, prefix, mode, skip_zero=False):
+    gW, gb = golden_grads(d, prefix)
+    worst = 0.0
+    for l in range(len(gW)):
+        lin = getattr(net, f"lin{l}")
+        for got, ref, nm in ((lin.weight.grad, gW[l], f"dW{l}"), (lin.bias.grad, gb[l], f"db{l}")):
+            assert got is not None, nm
+            if float(ref.norm()) < 1e-12:
+                assert float(got.norm()) < 1e-6, nm
+                continue
+            e = rel_err(got.cpu(), ref)
+            worst = max(worst, e)
+            assert e < TOL_GRAD_REL[mode], f"{nm}: rel err {e:.3e}"
+    return worst
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["softplus_skip_128x4.npz", "relu_tanh_128x3.npz"])
+def test_fused_igr_step_matches_reference(name, mode):
+    import sdf_representation_b200 as pkg
+
+    d = load_golden(name)
+    net = make_net(d, mode)
+    x = torch.from_numpy(d["x"]).to(dev())
+    y = torch.from_numpy(d["y"]).to(dev())
+    loss = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)(x, y, net, 0)
+    loss.backward()
+    el = abs(float(loss) - float(d["igr_loss"]))
+    worst = _check_grads(net, d, "igr_grad_", mode)
+    print(f"{name} {mode}: |loss - ref| = {el:.3e} (loss {float(loss):.6f}), worst grad rel err {worst:.3e}")
+    assert el < (2e-5 if mode == "parity" else 2e-3) * max(1.0, abs(float(d["igr_loss"])))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_generic_autograd_igr_matches_reference(mode):
+    """The reference's own loss arithmetic (model/losses.py:109-137) on top of the drop-in module's autograd path:
+    model(x), compute_normal-style autograd.grad(create_graph=True), loss.backward()."""
+    import sdf_representation_b200 as pkg
+
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, mode)
+    x = torch.from_numpy(d["x"]).to(dev())
+    y = torch.from_numpy(d["y"]).to(dev())
+    delta, tau, lam = 0.1, 1.0, 0.1
+    pred = torch.clamp(net(x), -delta, delta)
+    target = torch.clamp(y[:, 0], -delta, delta)
+    # O(N) form of the reference's [N,N] broadcast
+    data = (pred ** 2).mean() + (target ** 2).mean() - 2 * pred.mean() * target.mean()
+    xg = x.clone().requires_grad_(True)
+    out = net(xg)
+    normal = pkg.gradient(xg, out)
+    gnorm = normal.norm(2, dim=-1)
+    cos = torch.nn.functional.cosine_similarity(y[:, 1:], normal / normal.norm(), dim=-1)
+    loss = data + tau * ((1 - cos) ** 2).mean() + lam * ((gnorm - 1) ** 2).mean()
+    loss.backward()
+    el = abs(float(loss) - float(d["igr_loss"]))
+    worst = _check_grads(net, d, "igr_grad_", mode)
+    print(f"generic {mode}: |loss - ref| = {el:.3e}, worst grad rel err {worst:.3e}")
+    assert el < (2e-5 if mode == "parity" else 2e-3)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["softplus_skip_128x4.npz", "relu_tanh_128x3.npz"])
+def test_wsl2_matches_reference(name, mode):
+    import sdf_representation_b200 as pkg
+
+    d = load_golden(name)
+    net = make_net(d, mode)
+    x = torch.from_numpy(d["x"]).to(dev())
+    y = torch.from_numpy(d["y"]).to(dev())
+    loss = pkg.WeightedSmoothL2Loss(0.5, 0.1)(x, y, net, 0)
+    loss.backward()
+    el = abs(float(loss) - float(d["wsl2_loss"]))
+    worst = _check_grads(net, d, "wsl2_grad_", mode)
+    print(f"{name} {mode}: wsl2 |loss - ref| = {el:.3e}, worst grad rel err {worst:.3e}")
+    assert el < (2e-5 if mode == "parity" else 2e-3)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_pcd_step_matches_reference(mode):
+    import sdf_representation_b200 as pkg
+
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, mode)
+    x = torch.from_numpy(d["x"]).to(dev())
+    xp = torch.from_numpy(d["xp"]).to(dev())
+    crit = pkg.PointCloudLoss(0.1)
+    loss = crit(x, xp, net)
+    loss.backward()
+    el = abs(float(loss) - float(d["pcd_loss"]))
+    worst = _check_grads(net, d, "pcd_grad_", mode)
+    print(f"pcd {mode}: |loss - ref| = {el:.3e}, worst grad rel err {worst:.3e}")
+    assert el < (2e-5 if mode == "parity" else 2e-3)
+    terms = crit.last_terms.cpu().numpy()
+    assert abs(terms[0] - d["pcd_terms"][0]) < 2e-3 and abs(terms[1] - d["pcd_terms"][1]) < 2e-3
+
+
+def _full_net(mode):
+    import hashlib
+
+    import sdf_representation_b200 as pkg
+
+    d = load_golden("full_8x512_seed0.npz")
+    torch.manual_seed(0)
+    net = pkg.ImplicitNet(3, [512] * 8, (4,), 100.0, True, precision=mode)
+    h = hashlib.sha256()
+    for v in net.state_dict().values():
+        h.update(v.numpy().tobytes())
+    if h.hexdigest() != str(d["weights_sha256"]):
+        pytest.skip("torch build generates different seeded weights than the container that made the golden file")
+    return d, net.to(dev())
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_full_network_forward_gradient_loss(mode):
+    """BASELINE cfg 2 network (8x512, skip (4,), beta 100, seed-0 geometric init) on 512 reference points."""
+    import sdf_representation_b200 as pkg
+
+    d, net = _full_net(mode)
+    x = torch.from_numpy(d["x"]).to(dev())
+    y = torch.from_numpy(d["y"]).to(dev())
+    f, g = net.sdf_and_gradient(x)
+    ef = np.abs(f[:, 0].cpu().numpy() - d["f"]).max()
+    eg = np.abs(g.cpu().numpy() - d["g"]).max()
+    loss = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)(x, y, net, 0)
+    loss.backward()
+    norms = np.array([float(p.grad.norm()) for p in net.parameters()])
+    en = np.abs(norms / d["igr_grad_norms"] - 1).max()
+    print(f"8x512 {mode}: max|df| {ef:.3e} max|dg| {eg:.3e} loss {float(loss):.6f} vs {float(d['igr_loss']):.6f} grad-norm rel {en:.3e}")
+    assert ef < tol_f(mode) and eg < tol_g(mode)
+    assert abs(float(loss) - float(d["igr_loss"])) < (5e-5 if mode == "parity" else 5e-3)
+    assert en < TOL_GRAD_REL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_grid_eval_matches_reference_grid(mode):
+    from sdf_representation_b200 import inference
+
+    d, net = _full_net(mode)
+    vol = inference.grid_sdf(net, 9)
+    err = np.abs(vol.cpu().numpy() - d["grid9"]).max()
+    print(f"grid9 {mode}: max err {err:.3e}")
+    assert vol.shape == (9, 9, 9) and err < tol_f(mode)
+    # slab == slice of the whole volume, bit for bit (no collective, any slab split)
+    slab = inference.grid_sdf(net, 9, 3, 7)
+    assert torch.equal(slab, vol[3:7])
+    # grid path == point path on the reference's own coordinates, bit for bit
+    pts = orc.grid_points(9).to(dev())
+    with torch.no_grad():
+        assert torch.equal(net(pts)[:, 0], vol.reshape(-1))
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 1000, 20011])
+def test_ragged_sizes_and_tiling_independence(n):
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "fast")
+    W, b = golden_params(d)
+    g = torch.Generator().manual_seed(n)
+    x = torch.rand(n, 3, generator=g) * 2 - 1
+    f_ref, g_ref = orc.forward_and_gradient(W, b, x.double(), skip_of(d), float(d["beta"]))
+    f, gr = net.sdf_and_gradient(x.to(dev()))
+    assert (f[:, 0].cpu().double() - f_ref).abs().max() < TOL_FAST_F
+    assert (gr.cpu().double() - g_ref).abs().max() < TOL_FAST_G
+    with torch.no_grad():
+        f2 = net(x.to(dev()))
+    assert torch.equal(f2, f)  # forward-only program and forward+reverse program agree bit for bit
+    if n > 2:
+        k = n // 3
+        with torch.no_grad():
+            fa = net(x[:k].to(dev()))
+            fb = net(x[k:].to(dev()))
+        assert torch.equal(torch.cat([fa, fb]), f2)  # a point's value does not depend on its tile / position
+
+
+def test_empty_batch():
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "fast")
+    with torch.no_grad():
+        out = net(torch.empty(0, 3, device=dev()))
+    assert out.shape == (0, 1)
+
+
+def test_cpu_tensor_raises():
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "fast")
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(4, 3))
+
+
+def test_linearity_of_parameter_gradients():
+    """Size-independent property at a BASELINE-scale batch: grads(a*fbar1 + fbar2) == a*grads(fbar1) + grads(fbar2)."""
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "fast")
+    eng = net.engine()
+    n = 200_000
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1).to(dev())
+    f1 = torch.randn(n, generator=g).to(dev()) / n
+    f2 = torch.randn(n, generator=g).to(dev()) / n
+
+    def grads(fb):
+        eng.zero_grads()
+        eng.backward(x, fbar=fb)
+        return eng.read_grads().clone()
+
+    g1, g2, g12 = grads(f1), grads(f2), grads(2 * f1 + f2)
+    e = rel_err(g12, 2 * g1 + g2)
+    print(f"linearity rel err {e:.3e}")
+    assert e < 2e-2
+
+
+def test_octree_bit_exact_given_gpu_sdf():
+    from sdf_representation_b200 import inference
+
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "fast")
+    levels = inference.octree_build(net, max_level=6, refine_lvl_uni=2)
+    assert [l["keys"].numel() for l in levels[:3]] == [1, 8, 64]
+    for i, l in enumerate(levels):
+        keys = l["keys"].cpu().numpy().astype(np.uint64)
+        sdf = l["sdf"].cpu().numpy()
+        # the kernel evaluated the network at the oracle's cell centres
+        centers = orc.octree_centers(keys, l["level"])
+        with torch.no_grad():
+            f_pts = net(torch.from_numpy(centers).to(dev()))[:, 0].cpu().numpy()
+        assert np.array_equal(f_pts, sdf)
+        flags = orc.octree_flags(sdf, l["level"], np.sqrt(3.0) / 2)
+        if l["level"] < 2:
+            flags = np.ones_like(flags)
+        assert np.array_equal(flags, l["flags"].cpu().numpy())
+        if i + 1 < len(levels):
+            assert np.array_equal(orc.octree_children(keys, flags), levels[i + 1]["keys"].cpu().numpy().astype(np.uint64))
+    # subtree sharding: union over ranks == single-rank result
+    parts = [inference.octree_build(net, 6, 2, rank=r, world=3) for r in range(3)]
+    last = np.sort(np.concatenate([p[-1]["keys"].cpu().numpy() for p in parts]))
+    assert np.array_equal(last, np.sort(levels[-1]["keys"].cpu().numpy()))
+
+
+def test_mc_classify_bit_exact():
+    from sdf_representation_b200 import inference
+
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "fast")
+    vol = inference.grid_sdf(net, 33)
+    cases, active = inference.mc_classify(vol)
+    rc, ra = orc.mc_cases(vol.cpu().numpy())
+    assert np.array_equal(cases.cpu().numpy(), rc)
+    assert np.array_equal(active.cpu().numpy(), ra)
+    assert 0 < ra.size < rc.size
+
+
+def test_adam_step_matches_torch():
+    from sdf_representation_b200 import engine
+
+    torch.manual_seed(0)
+    p = torch.randn(100_003, device=dev())
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=4e-4)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn_like(p)
+        ref.grad = g.clone()
+        opt.step()
+        engine.adam_step(p, g, m, v, 4e-4, step)
+    assert (p - ref.detach()).abs().max() < 1e-6
+
+
+def test_training_curve_tracks_reference_arithmetic():
+    """Loss curve over a few Adam steps, fused CUDA step vs the oracle's restatement from identical weights/batches."""
+    import sdf_representation_b200 as pkg
+
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "parity")
+    W, b = golden_params(d)
+    x = torch.from_numpy(d["x"])
+    y = torch.from_numpy(d["y"])
+    opt = torch.optim.Adam(net.parameters(), lr=4e-4)
+    crit = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)
+    mW = [torch.zeros_like(w) for w in W]; vW = [torch.zeros_like(w) for w in W]
+    mb = [torch.zeros_like(w) for w in b]; vb = [torch.zeros_like(w) for w in b]
+    for step in range(1, 6):
+        opt.zero_grad()
+        loss = crit(x.to(dev()), y.to(dev()), net, step)
+        loss.backward()
+        opt.step()
+        lref, _, dW, db = orc.igr_loss_and_grads(W, b, x.double(), y.double(), skip_of(d), float(d["beta"]))
+        for l in range(len(W)):
+            W[l], mW[l], vW[l] = orc.adam_step(W[l], dW[l], mW[l], vW[l], 4e-4, step)
+            b[l], mb[l], vb[l] = orc.adam_step(b[l], db[l], mb[l], vb[l], 4e-4, step)
+        print(f"step {step}: loss {float(loss):.6f} oracle {float(lref):.6f}")
+        assert abs(float(loss) - float(lref)) < 1e-3 * max(1.0, abs(float(lref)))
