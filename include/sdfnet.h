@@ -112,6 +112,14 @@ int sdfnet_adam_step(float* params, const float* grads, float* exp_avg, float* e
 int sdfnet_mc_classify(const float* sdf, int32_t nx, int32_t ny, int32_t nz, uint8_t* case_index,
                        int64_t* active_cells, int64_t* n_active, void* stream);
 
+/* Instrumentation (no reference counterpart; used by bench.py): kernels launched through this handle so far, and
+ * CUDA-event timing of each kernel class on its launch stream.  Classes: 0 = layer chain forward (+ reverse),
+ * 1 = layer chain tangent + adjoint, 2 = weight-gradient GEMM, 3 = everything else.  sdfnet_profile_read waits for the
+ * recorded events and returns accumulated milliseconds and launch counts since sdfnet_profile_enable(h, 1). */
+int64_t sdfnet_launch_count(sdfnet_t h);
+int sdfnet_profile_enable(sdfnet_t h, int32_t on);
+int sdfnet_profile_read(sdfnet_t h, double* ms4, int64_t* launches4);
+
 /* Octree refinement (build-defined): children keys of the flagged cells, in order. */
 int sdfnet_octree_refine(const uint64_t* keys, const uint8_t* flags, int64_t count, uint64_t* child_keys,
                          int64_t* n_children, void* stream);

@@ -10,18 +10,20 @@
 #include "sdf_internal.h"
 
 namespace sdf {
-cudaError_t launch_chain(const ChainParams& p, int dtype, int num_sms, cudaStream_t stream);
+cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int num_sms, cudaStream_t stream);
 cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
-                                int k16, int kind, float scale, int dtype, cudaStream_t stream);
+                                int k16, int kind, float scale, int dtype, int split, cudaStream_t stream);
 cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream);
-cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int num_sms, cudaStream_t stream);
+cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
                              float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
-                             int relu_tanh, float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
                              cudaStream_t stream);
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
-                             float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
                              cudaStream_t stream);
+cudaError_t launch_absmax(const float* v, int64_t n, unsigned* absmax, cudaStream_t stream);
+cudaError_t launch_seed_scale(unsigned* absmax, float* scale, cudaStream_t stream);
 cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream);
 cudaError_t launch_tanh_seeds(const float* f, const float* g, const float* fbar_in, const float* gbar_in, int64_t n,
                               float* fbar, float* gbar, cudaStream_t stream);
@@ -57,7 +59,7 @@ int fail(int code, const char* fmt, ...) {
 enum : int { PK_F0 = 0, PK_FH = 1, PK_FL = 2, PK_RH = 3, PK_R0 = 4 };
 
 struct StepImage {  // shape of one packed step image
-  int n_groups, ng, kchunks, k16;
+  int n_groups, ng, kchunks, k16, a_chunks, split;
   uint32_t chunk_bytes, off;
   uint32_t bytes() const { return static_cast<uint32_t>(n_groups) * kchunks * chunk_bytes; }
 };
@@ -80,7 +82,10 @@ struct GradLayout {
 struct sdfnet_handle {
   sdfnet_desc d;
   int H, L, skip, num_sms;
-  bool relu;
+  bool relu, parity;
+  int pts;                 // points per tile: 128 (fast) or 64 (parity)
+  float* scale_dev = nullptr;      // [0] seed multiplier (power of two), [1] its inverse
+  unsigned* absmax_dev = nullptr;  // running max |seed| of the current chunk
   uint8_t* wpack = nullptr;
   size_t wpack_bytes = 0;
   float* bias = nullptr;
@@ -97,19 +102,48 @@ struct sdfnet_handle {
   const void* items_ws = nullptr;
   int items_tiles = -1;
   int items_so = -1;
-  float* seeds = nullptr;  // scratch for f, g, fbar, gbar of one chunk (allocated on demand)
-  int64_t seeds_cap = 0;
-  float seed_scale = 1.f;
+  // instrumentation: kernels launched through this handle, and (when enabled) CUDA-event timing per kernel class
+  int64_t launches = 0;
+  bool prof_on = false;
+  struct ProfRec { int cls; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_n[4] = {0, 0, 0, 0};
 };
+
+namespace {
+enum : int { PC_CHAIN_FG = 0, PC_CHAIN_TA = 1, PC_DW = 2, PC_OTHER = 3 };
+// RAII bracket around one kernel launch: counts it and, in profiling mode, records events on the launch stream
+struct Launch {
+  sdfnet_handle* h; cudaStream_t st; int idx = -1;
+  Launch(sdfnet_handle* h_, int cls, cudaStream_t st_, int count = 1) : h(h_), st(st_) {
+    h->launches += count;
+    if (!h->prof_on) return;
+    sdfnet_handle::ProfRec r; r.cls = cls;
+    for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+      if (!h->ev_pool.empty()) { *e = h->ev_pool.back(); h->ev_pool.pop_back(); }
+      else if (cudaEventCreate(e) != cudaSuccess) return;
+    }
+    cudaEventRecord(r.e0, st);
+    h->prof.push_back(r);
+    idx = static_cast<int>(h->prof.size()) - 1;
+  }
+  ~Launch() { if (idx >= 0) cudaEventRecord(h->prof[idx].e1, st); }
+};
+}  // namespace
 
 extern "C" const char* sdfnet_last_error(void) { return g_err; }
 
-static StepImage make_image(int N, int K16total, int kchunk_k16, uint32_t& off) {
+// split: parity-mode image = hi chunks followed by lo chunks of the same weights (A chunk index wraps)
+static StepImage make_image(int N, int K16total, int kchunk_k16, bool split, uint32_t& off) {
   StepImage s;
   s.ng = N < 256 ? N : 256;
   s.n_groups = N / s.ng;
   s.k16 = kchunk_k16;
-  s.kchunks = K16total / kchunk_k16;
+  s.a_chunks = K16total / kchunk_k16;
+  s.split = split ? 1 : 0;
+  s.kchunks = s.a_chunks * (split ? 2 : 1);
   s.chunk_bytes = static_cast<uint32_t>(s.ng) * 16u * 2u * kchunk_k16;
   s.off = off;
   off += s.bytes();
@@ -126,7 +160,7 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   if (desc->skip_layer < 0 || desc->skip_layer == 1 || desc->skip_layer >= desc->num_hidden)
     return fail(1, "sdfnet_create: skip layer must be 0 (none) or in [2,%d) (got %d)", desc->num_hidden, desc->skip_layer);
   if (desc->dtype != DT_BF16 && desc->dtype != DT_FP16) return fail(1, "sdfnet_create: dtype must be 0 (bf16) or 1 (fp16)");
-  if (desc->precision != 0) return fail(1, "sdfnet_create: precision %d not available in this build", desc->precision);
+  if (desc->precision != 0 && desc->precision != 1) return fail(1, "sdfnet_create: precision must be 0 (fast) or 1 (parity)");
   if (!(desc->beta >= 0.f)) return fail(1, "sdfnet_create: beta must be >= 0");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -143,16 +177,19 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   h->L = desc->num_hidden;
   h->skip = desc->skip_layer;
   h->relu = desc->beta == 0.f;
+  h->parity = desc->precision == 1;
+  h->pts = h->parity ? kParityPoints : kTileRows;
   h->num_sms = prop.multiProcessorCount;
   const int H = h->H, L = h->L;
   uint32_t off = 0;
   h->F.resize(L + 1);
   h->R.resize(L);
-  h->F[0] = make_image(H, 1, 1, off);                     // K = 16 (split input block)
-  for (int l = 1; l < L; ++l) h->F[l] = make_image(H, H / 16, 4, off);
-  h->F[L] = make_image(16, H / 16, H / 16, off);          // N = 16 (row 0 = lin_L)
-  for (int l = L - 1; l >= 1; --l) h->R[l] = make_image(H, H / 16, 4, off);
-  h->R[0] = make_image(16, H / 16, H / 16, off);          // N = 16 (rows 0..2 = d/dx)
+  const bool sp = h->parity;
+  h->F[0] = make_image(H, 1, 1, false, off);                  // K = 16 (input block, already split along K)
+  for (int l = 1; l < L; ++l) h->F[l] = make_image(H, H / 16, 4, sp, off);
+  h->F[L] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (row 0 = lin_L)
+  for (int l = L - 1; l >= 1; --l) h->R[l] = make_image(H, H / 16, 4, sp, off);
+  h->R[0] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (rows 0..2 = d/dx)
   h->wpack_bytes = off;
   CU(cudaMalloc(&h->wpack, h->wpack_bytes));
   CU(cudaMalloc(&h->bias, sizeof(float) * (L + 1) * H));
@@ -163,6 +200,13 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   h->acc_floats = n_main + n_zx + 3 * 16 * static_cast<size_t>(H);
   CU(cudaMalloc(&h->acc, sizeof(float) * h->acc_floats));
   CU(cudaMalloc(&h->fbar_sum, sizeof(double)));
+  CU(cudaMalloc(&h->scale_dev, 2 * sizeof(float)));
+  CU(cudaMalloc(&h->absmax_dev, sizeof(unsigned)));
+  CU(cudaMemset(h->absmax_dev, 0, sizeof(unsigned)));
+  {
+    const float one[2] = {1.f, 1.f};
+    CU(cudaMemcpy(h->scale_dev, one, sizeof(one), cudaMemcpyHostToDevice));
+  }
   CU(cudaMemset(h->acc, 0, sizeof(float) * h->acc_floats));
   CU(cudaMemset(h->fbar_sum, 0, sizeof(double)));
   GradLayout& gl = h->gl;
@@ -191,8 +235,11 @@ extern "C" int sdfnet_destroy(sdfnet_t h) {
   cudaFree(h->w_last);
   cudaFree(h->acc);
   cudaFree(h->fbar_sum);
+  cudaFree(h->scale_dev);
+  cudaFree(h->absmax_dev);
   cudaFree(h->items_dev);
-  cudaFree(h->seeds);
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -209,20 +256,21 @@ extern "C" int sdfnet_pack_weights(sdfnet_t h, const float* const* W, const floa
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int H = h->H, L = h->L, dt = h->d.dtype;
   const float c = static_cast<float>(1.0 / std::sqrt(2.0));
+  Launch lp(h, PC_OTHER, stream, 3 * (L + 1));
   for (int l = 0; l <= L; ++l) {
     if (!W[l] || !b[l]) return fail(1, "sdfnet_pack_weights: null parameter pointer for layer %d", l);
     const StepImage& s = h->F[l];
     const int kind = l == 0 ? PK_F0 : (l == L ? PK_FL : PK_FH);
     const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
     CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           kind, scale, dt, stream));
+                           kind, scale, dt, s.split, stream));
     CU(launch_pack_bias(b[l], out_dim_of(h, l), h->bias + static_cast<size_t>(l) * H, H, stream));
   }
   for (int l = L - 1; l >= 0; --l) {
     const StepImage& s = h->R[l];
     const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
     CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           l == 0 ? PK_R0 : PK_RH, scale, dt, stream));
+                           l == 0 ? PK_R0 : PK_RH, scale, dt, s.split, stream));
   }
   CU(cudaMemcpyAsync(h->w_last, W[L], sizeof(float) * H, cudaMemcpyDeviceToDevice, stream));
   return 0;
@@ -236,10 +284,10 @@ static void add_step(ChainParams& p, int epi, int layer, const StepImage* img) {
   s.epi = epi;
   s.layer = layer;
   if (img) {
-    s.n_groups = img->n_groups; s.ng = img->ng; s.kchunks = img->kchunks; s.k16 = img->k16;
+    s.n_groups = img->n_groups; s.ng = img->ng; s.kchunks = img->kchunks; s.k16 = img->k16; s.a_chunks = img->a_chunks;
     s.chunk_bytes = img->chunk_bytes; s.w_off = img->off;
   } else {
-    s.n_groups = 0; s.ng = 0; s.kchunks = 0; s.k16 = 0; s.chunk_bytes = 0; s.w_off = 0;
+    s.n_groups = 0; s.ng = 0; s.kchunks = 0; s.k16 = 0; s.a_chunks = 1; s.chunk_bytes = 0; s.w_off = 0;
   }
 }
 static void base_params(const sdfnet_handle* h, ChainParams& p) {
@@ -301,7 +349,7 @@ void carve(const sdfnet_handle* h, int mode, uint8_t* ws, size_t tiles, Spill& s
 
 extern "C" size_t sdfnet_workspace_bytes(sdfnet_t h, int64_t n_points, int32_t mode) {
   if (!h || n_points <= 0) return 0;
-  const size_t tiles = static_cast<size_t>((n_points + kTileRows - 1) / kTileRows);
+  const size_t tiles = static_cast<size_t>((n_points + h->pts - 1) / h->pts);
   return tiles * per_tile_bytes(h, mode) + 1024;
 }
 
@@ -318,9 +366,10 @@ static uint8_t* align_ws(void* ws, size_t& bytes) {
 // ------------------------------------------------------------------------------------------------
 static int run_forward(sdfnet_t h, ChainParams& p, int64_t n, cudaStream_t stream) {
   p.n = n;
-  p.n_tiles = static_cast<int>((n + kTileRows - 1) / kTileRows);
+  p.n_tiles = static_cast<int>((n + h->pts - 1) / h->pts);
   prog_forward(h, p);
-  CU(launch_chain(p, h->d.dtype, h->num_sms, stream));
+  Launch lr(h, PC_CHAIN_FG, stream);
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 
@@ -376,7 +425,8 @@ extern "C" int sdfnet_octree_level(sdfnet_t h, const uint64_t* keys, int64_t cou
   p.f_out = sdf_out;
   if (int rc = run_forward(h, p, count, static_cast<cudaStream_t>(stream))) return rc;
   if (refine_flags) {
-    const float thresh = band * ldexpf(2.f, -level);  // band * h_level, one fp32 rounding (oracle/octree.py)
+    const float thresh = band * ldexpf(2.f, -level);  // band * h_level, one fp32 rounding (oracle/sdf_oracle.py)
+    Launch lf(h, PC_OTHER, static_cast<cudaStream_t>(stream));
     CU(launch_octree_flags(sdf_out, count, thresh, refine_flags, static_cast<cudaStream_t>(stream)));
   }
   return 0;
@@ -391,7 +441,7 @@ extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float*
   size_t cap_tiles = ws_bytes / ptb;
   if (!ws_ || cap_tiles == 0) return fail(1, "sdfnet_forward_grad: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, ptb);
   if (cap_tiles > (1u << 22)) cap_tiles = 1u << 22;
-  const int64_t chunk = static_cast<int64_t>(cap_tiles) * kTileRows;
+  const int64_t chunk = static_cast<int64_t>(cap_tiles) * h->pts;
   for (int64_t o = 0; o < n; o += chunk) {
     const int64_t m = n - o < chunk ? n - o : chunk;
     ChainParams p;
@@ -401,14 +451,15 @@ extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float*
     p.f_out = sdf_out ? sdf_out + o : nullptr;
     p.g_out = grad_out + o * 3;
     p.n = m;
-    p.n_tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    p.n_tiles = static_cast<int>((m + h->pts - 1) / h->pts);
     Spill s;
     carve(h, 0, ws, p.n_tiles, s);
     p.Aimg = s.A;
     p.flags |= FL_SPILL_A;
     prog_forward(h, p);
     prog_reverse(h, p);
-    CU(launch_chain(p, h->d.dtype, h->num_sms, static_cast<cudaStream_t>(stream)));
+    Launch lr(h, PC_CHAIN_FG, static_cast<cudaStream_t>(stream));
+    CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, static_cast<cudaStream_t>(stream)));
   }
   return 0;
 }
@@ -424,7 +475,8 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   const uint32_t xb = 2 * kGranuleBytes;
   const GradLayout& gl = h->gl;
   if (h->items_ws == s.A && h->items_tiles == tiles && h->items_so == (second_order ? 1 : 0) && h->items_n > 0) {
-    CU(launch_dw(h->items_dev, h->items_n, h->d.dtype, h->num_sms, stream));
+    Launch lr(h, PC_DW, stream);
+    CU(launch_dw(h->items_dev, h->items_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
     return 0;
   }
   std::vector<DwItem> items;
@@ -450,7 +502,7 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
           d.a_tstride = ib; d.b_tstride = ib;
           d.a_off = static_cast<uint32_t>(mb) * 16 * kGranuleBytes;
           d.b_off = static_cast<uint32_t>(nh) * (nb / 8) * kGranuleBytes;
-          d.n = nb; d.tile0 = t0; d.tile1 = t1; d.out_ld = H;
+          d.n = nb; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1;
           d.out = gl.main_acc + (static_cast<size_t>(l - 1) * H + static_cast<size_t>(nh) * nb) * H + mb * 128;
           items.push_back(d);
         }
@@ -460,24 +512,24 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
       for (int l = 0; l < L; ++l) {   // Zbar_l^T . Xblock -> biases (col 15) and, for l = 0, dW_0 term 1
         DwItem d{};
         d.A1 = s.Z + arr * l; d.B1 = s.X; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
-        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H;
+        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1;
         d.out = gl.zx_acc + static_cast<size_t>(l) * 16 * H + mb * 128;
         items.push_back(d);
       }
       {  // a_{L-1}^T . Sblock -> dW_L term 1
         DwItem d{};
         d.A1 = s.A + arr * (L - 1); d.B1 = s.S; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
-        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.out = gl.as_acc + mb * 128;
+        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1; d.out = gl.as_acc + mb * 128;
         items.push_back(d);
       }
       if (second_order) {
         DwItem d{};  // q_0^T . Gblock -> dW_0 term 2
         d.A1 = s.Q; d.B1 = s.G; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
-        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.out = gl.qg_acc + mb * 128;
+        d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1; d.out = gl.qg_acc + mb * 128;
         items.push_back(d);
         DwItem e{};  // adot_{L-1}^T . Xblock -> dW_L term 2 (col 15)
         e.A1 = s.AD + arr * (L - 1); e.B1 = s.X; e.a_tstride = ib; e.b_tstride = xb; e.a_off = aoff; e.b_off = 0;
-        e.n = 16; e.tile0 = t0; e.tile1 = t1; e.out_ld = H; e.out = gl.adx_acc + mb * 128;
+        e.n = 16; e.tile0 = t0; e.tile1 = t1; e.out_ld = H; e.inv_mult = h->scale_dev + 1; e.out = gl.adx_acc + mb * 128;
         items.push_back(e);
       }
     }
@@ -495,7 +547,8 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   CU(cudaMemcpyAsync(h->items_dev, items.data(), sizeof(DwItem) * n_items, cudaMemcpyHostToDevice, stream));
   CU(cudaStreamSynchronize(stream));
   h->items_n = n_items; h->items_ws = s.A; h->items_tiles = tiles; h->items_so = second_order ? 1 : 0;
-  CU(launch_dw(h->items_dev, n_items, h->d.dtype, h->num_sms, stream));
+  Launch lr(h, PC_DW, stream);
+  CU(launch_dw(h->items_dev, n_items, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 
@@ -506,14 +559,15 @@ int run_fg(sdfnet_t h, const float* x, int64_t m, const Spill& s, bool need_g, c
   p.src = SRC_POINTS;
   p.x = x;
   p.n = m;
-  p.n_tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+  p.n_tiles = static_cast<int>((m + h->pts - 1) / h->pts);
   p.f_out = s.f;
   p.g_out = need_g ? s.g : nullptr;
   p.Aimg = s.A; p.Qimg = s.Q; p.Ximg = s.X;
   p.flags |= FL_SPILL_A | FL_SPILL_X | (need_g ? FL_SPILL_Q : 0u);
   prog_forward(h, p);
   if (need_g) prog_reverse(h, p);
-  CU(launch_chain(p, h->d.dtype, h->num_sms, stream));
+  Launch lr(h, PC_CHAIN_FG, stream);
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 // tangent (+adjoint) sweeps over one chunk
@@ -521,21 +575,22 @@ int run_ta(sdfnet_t h, int64_t m, const Spill& s, const float* fbar, const float
   ChainParams p;
   base_params(h, p);
   p.n = m;
-  p.n_tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
-  p.fbar = fbar; p.gbar = gbar;
+  p.n_tiles = static_cast<int>((m + h->pts - 1) / h->pts);
+  p.fbar = fbar; p.gbar = gbar; p.seed_mult = h->scale_dev;
   p.Aimg = s.A; p.Qimg = s.Q; p.ADimg = s.AD; p.Uimg = s.U; p.Zimg = s.Z; p.Ximg = s.X; p.Gimg = s.G; p.Simg = s.S;
   if (gbar) {
     p.flags |= FL_TANGENT;
     prog_tangent(h, p);
   }
   prog_adjoint(h, p);
-  CU(launch_chain(p, h->d.dtype, h->num_sms, stream));
+  Launch lr(h, PC_CHAIN_TA, stream);
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 int64_t chunk_points(sdfnet_t h, size_t ws_bytes) {
   size_t cap_tiles = ws_bytes / per_tile_bytes(h, 1);
   if (cap_tiles > (1u << 22)) cap_tiles = 1u << 22;
-  return static_cast<int64_t>(cap_tiles) * kTileRows;
+  return static_cast<int64_t>(cap_tiles) * h->pts;
 }
 }  // namespace
 
@@ -549,8 +604,9 @@ extern "C" int sdfnet_zero_grads(sdfnet_t h, void* stream) {
 extern "C" int sdfnet_read_grads(sdfnet_t h, float* grads, float scale, void* stream) {
   if (!h || !grads) return fail(1, "sdfnet_read_grads: null argument");
   const GradLayout& gl = h->gl;
+  Launch lr(h, PC_OTHER, static_cast<cudaStream_t>(stream));
   CU(launch_unpack_grads(gl.H, gl.L, gl.skip, gl.main_acc, gl.zx_acc, gl.qg_acc, gl.as_acc, gl.adx_acc, gl.fbar_sum,
-                         gl.num_params, grads, scale / h->seed_scale, static_cast<cudaStream_t>(stream)));
+                         gl.num_params, grads, scale, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -565,7 +621,7 @@ extern "C" int sdfnet_backward(sdfnet_t h, const float* x, int64_t n, const floa
   if (chunk <= 0) return fail(1, "sdfnet_backward: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, per_tile_bytes(h, 1));
   for (int64_t o = 0; o < n; o += chunk) {
     const int64_t m = n - o < chunk ? n - o : chunk;
-    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    const int tiles = static_cast<int>((m + h->pts - 1) / h->pts);
     Spill s;
     carve(h, 1, ws, tiles, s);
     // the ReLU/tanh network needs f (and g) to move the seeds through the output tanh
@@ -579,6 +635,12 @@ extern "C" int sdfnet_backward(sdfnet_t h, const float* x, int64_t n, const floa
       gb = gbar ? s.gbar : nullptr;
     }
     if (fb) CU(launch_sum(fb, m, h->fbar_sum, stream));
+    {
+      Launch ls(h, PC_OTHER, stream, 2 + (fb ? 1 : 0) + (gb ? 1 : 0));
+      if (fb) CU(launch_absmax(fb, m, h->absmax_dev, stream));
+      if (gb) CU(launch_absmax(gb, 3 * m, h->absmax_dev, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+    }
     if (int rc = run_ta(h, m, s, fb, gb, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, gbar != nullptr, stream)) return rc;
   }
@@ -596,13 +658,17 @@ extern "C" int sdfnet_train_step_igr(sdfnet_t h, const float* x, const float* y,
   if (chunk <= 0) return fail(1, "sdfnet_train_step_igr: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, per_tile_bytes(h, 1));
   for (int64_t o = 0; o < n; o += chunk) {
     const int64_t m = n - o < chunk ? n - o : chunk;
-    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    const int tiles = static_cast<int>((m + h->pts - 1) / h->pts);
     Spill s;
     carve(h, 1, ws, tiles, s);
     if (int rc = run_fg(h, x + o * 3, m, s, true, stream)) return rc;
-    CU(launch_igr_seeds(s.f, s.g, y + o * 4, m, cfg->delta, cfg->tau, cfg->lambda_g, cfg->regularizer_threshold,
-                        cfg->mean_t, cfg->mean_t_dev, 1.0 / static_cast<double>(cfg->n_global), cfg->data_term, h->relu ? 1 : 0,
-                        h->seed_scale, s.fbar, s.gbar, loss_sums, h->fbar_sum, stream));
+    {
+      Launch ls(h, PC_OTHER, stream, 3);
+      CU(launch_igr_seeds(s.f, s.g, y + o * 4, m, cfg->delta, cfg->tau, cfg->lambda_g, cfg->regularizer_threshold,
+                          cfg->mean_t, cfg->mean_t_dev, 1.0 / static_cast<double>(cfg->n_global), cfg->data_term, h->relu ? 1 : 0,
+                          h->absmax_dev, s.fbar, s.gbar, loss_sums, h->fbar_sum, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+    }
     if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, true, stream)) return rc;
   }
@@ -620,27 +686,62 @@ extern "C" int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int6
   // surface points: L += mean |f|   (first order: forward + adjoint + dW term 1)
   for (int64_t o = 0; x && o < n; o += chunk) {
     const int64_t m = n - o < chunk ? n - o : chunk;
-    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    const int tiles = static_cast<int>((m + h->pts - 1) / h->pts);
     Spill s;
     carve(h, 1, ws, tiles, s);
     if (int rc = run_fg(h, x + o * 3, m, s, false, stream)) return rc;
-    CU(launch_pcd_seeds(s.f, nullptr, m, 0, 1.f / static_cast<float>(n_global), h->relu ? 1 : 0, h->seed_scale, s.fbar,
-                        nullptr, loss_sums, h->fbar_sum, stream));
+    {
+      Launch ls(h, PC_OTHER, stream, 3);
+      CU(launch_pcd_seeds(s.f, nullptr, m, 0, 1.f / static_cast<float>(n_global), h->relu ? 1 : 0, h->absmax_dev, s.fbar,
+                          nullptr, loss_sums, h->fbar_sum, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+    }
     if (int rc = run_ta(h, m, s, s.fbar, nullptr, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, false, stream)) return rc;
   }
   // perturbed points: L += lambda mean (|grad f| - 1)^2
   for (int64_t o = 0; xp && o < m_; o += chunk) {
     const int64_t m = m_ - o < chunk ? m_ - o : chunk;
-    const int tiles = static_cast<int>((m + kTileRows - 1) / kTileRows);
+    const int tiles = static_cast<int>((m + h->pts - 1) / h->pts);
     Spill s;
     carve(h, 1, ws, tiles, s);
     if (int rc = run_fg(h, xp + o * 3, m, s, true, stream)) return rc;
-    CU(launch_pcd_seeds(s.f, s.g, m, 1, lambda_g / static_cast<float>(m_global), h->relu ? 1 : 0, h->seed_scale, s.fbar,
-                        s.gbar, loss_sums, h->fbar_sum, stream));
+    {
+      Launch ls(h, PC_OTHER, stream, 3);
+      CU(launch_pcd_seeds(s.f, s.g, m, 1, lambda_g / static_cast<float>(m_global), h->relu ? 1 : 0, h->absmax_dev, s.fbar,
+                          s.gbar, loss_sums, h->fbar_sum, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+    }
     if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, true, stream)) return rc;
   }
+  return 0;
+}
+
+extern "C" int64_t sdfnet_launch_count(sdfnet_t h) { return h ? h->launches : -1; }
+
+extern "C" int sdfnet_profile_enable(sdfnet_t h, int32_t on) {
+  if (!h) return fail(1, "sdfnet_profile_enable: null handle");
+  h->prof_on = on != 0;
+  if (on) {
+    for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  }
+  return 0;
+}
+
+extern "C" int sdfnet_profile_read(sdfnet_t h, double* ms4, int64_t* launches4) {
+  if (!h || !ms4 || !launches4) return fail(1, "sdfnet_profile_read: null argument");
+  for (auto& r : h->prof) {
+    CU(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    h->prof_ms[r.cls] += ms;
+    h->prof_n[r.cls] += 1;
+    h->ev_pool.push_back(r.e0);
+    h->ev_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  for (int i = 0; i < 4; ++i) { ms4[i] = h->prof_ms[i]; launches4[i] = h->prof_n[i]; }
   return 0;
 }
 

@@ -27,8 +27,9 @@ __device__ __forceinline__ uint16_t bits16(float v, int dtype) {
 // ------------------------------------------------------------------------------------------------
 enum : int { PK_F0 = 0, PK_FH = 1, PK_FL = 2, PK_RH = 3, PK_R0 = 4 };
 
+// split != 0 (parity mode): kchunks counts hi chunks followed by lo chunks, lo = rnd16(v - rnd16(v)).
 __global__ void pack_weights_kernel(const float* __restrict__ W, int out_dim, int in_dim, uint16_t* __restrict__ dst,
-                                    int n_groups, int ng, int kchunks, int k16, int kind, float scale, int dtype) {
+                                    int n_groups, int ng, int kchunks, int k16, int kind, float scale, int dtype, int split) {
   const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -36,9 +37,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, int out_dim, in
     const int e = static_cast<int>(t % 8); t /= 8;
     const int row = static_cast<int>(t % ng); t /= ng;
     const int gr = static_cast<int>(t % (2 * k16)); t /= (2 * k16);
-    const int kc = static_cast<int>(t % kchunks); t /= kchunks;
+    int kc = static_cast<int>(t % kchunks); t /= kchunks;
     const int g = static_cast<int>(t);
     const int n = g * ng + row;
+    bool lo_part = false;
+    if (split) {
+      lo_part = kc >= kchunks / 2;
+      kc %= kchunks / 2;
+    }
     const int k = (kc * 2 * k16 + gr) * 8 + e;
     float v = 0.f;
     switch (kind) {
@@ -62,6 +68,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, int out_dim, in
         if (n < in_dim && k < out_dim) v = W[k * in_dim + n];
         break;
     }
+    if (lo_part) v = v - rnd16(v, dtype);
     dst[idx] = bits16(v, dtype);
   }
 }
@@ -71,13 +78,13 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, int out_dim, float
 }
 
 cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
-                                int k16, int kind, float scale, int dtype, cudaStream_t stream) {
+                                int k16, int kind, float scale, int dtype, int split, cudaStream_t stream) {
   const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
   if (blocks < 1) blocks = 1;
   pack_weights_kernel<<<blocks, 256, 0, stream>>>(W, out_dim, in_dim, static_cast<uint16_t*>(dst), n_groups, ng, kchunks,
-                                                  k16, kind, scale, dtype);
+                                                  k16, kind, scale, dtype, split);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream) {
@@ -120,9 +127,15 @@ __device__ __forceinline__ void block_accumulate(float (&v)[NS], double* sums) {
 struct IgrCfgDev {
   float delta, tau, lambda_g, thr, mean_t, inv_n;
   int data_term, relu_tanh;
-  float seed_scale;
   const float* mean_t_dev;
+  unsigned* absmax;   // running max |seed| (float bits; non-negative floats order like unsigned ints)
 };
+
+__device__ __forceinline__ void block_absmax(float m, unsigned* absmax) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m <= 3.0e38f) atomicMax(absmax, __float_as_uint(m));
+}
 
 // reference model/losses.py:109-137 (IGRLOSS.forward) differentiated by hand:
 //   p = clamp(f, +-delta), t = clamp(S, +-delta), m = |t| < thr
@@ -132,6 +145,7 @@ __global__ void igr_seeds_kernel(const float* __restrict__ f, const float* __res
                                  long n, IgrCfgDev c, float* __restrict__ fbar, float* __restrict__ gbar,
                                  double* __restrict__ sums) {
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float amax = 0.f;
   if (c.mean_t_dev) c.mean_t = __ldg(c.mean_t_dev);
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float fi = f[i];
@@ -171,18 +185,21 @@ __global__ void igr_seeds_kernel(const float* __restrict__ f, const float* __res
       fb = fb * d - 2.f * fi * (bx * gx + by * gy + bz * gz);
       bx *= d; by *= d; bz *= d;
     }
-    fbar[i] = fb * c.seed_scale;
-    gbar[3 * i] = bx * c.seed_scale; gbar[3 * i + 1] = by * c.seed_scale; gbar[3 * i + 2] = bz * c.seed_scale;
+    fbar[i] = fb;
+    gbar[3 * i] = bx; gbar[3 * i + 1] = by; gbar[3 * i + 2] = bz;
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(fb), fabsf(bx)), fmaxf(fabsf(by), fabsf(bz))));
   }
+  block_absmax(amax, c.absmax);
   block_accumulate<8>(acc, sums);
 }
 
 // reference executor/executordistributed.py:73-79:  which = 0: surface points, L += mean |f|  (fbar = sign(f)/N);
 // which = 1: perturbed points, L += lambda mean (|g|-1)^2  (gbar = (lambda/M) 2 (|g|-1) g/|g|).  coef = 1/N or lambda/M.
 __global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, long n, int which, float coef,
-                                 int relu_tanh, float seed_scale, float* __restrict__ fbar, float* __restrict__ gbar,
+                                 int relu_tanh, unsigned* __restrict__ absmax, float* __restrict__ fbar, float* __restrict__ gbar,
                                  double* __restrict__ sums) {
   float acc[1] = {0.f};
+  float amax = 0.f;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float fi = f[i];
     float fb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
@@ -202,9 +219,11 @@ __global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __res
       fb = fb * d - 2.f * fi * (bx * gx + by * gy + bz * gz);
       bx *= d; by *= d; bz *= d;
     }
-    fbar[i] = fb * seed_scale;
-    if (gbar) { gbar[3 * i] = bx * seed_scale; gbar[3 * i + 1] = by * seed_scale; gbar[3 * i + 2] = bz * seed_scale; }
+    fbar[i] = fb;
+    if (gbar) { gbar[3 * i] = bx; gbar[3 * i + 1] = by; gbar[3 * i + 2] = bz; }
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(fb), fabsf(bx)), fmaxf(fabsf(by), fabsf(bz))));
   }
+  block_absmax(amax, absmax);
   block_accumulate<1>(acc, sums + which);
 }
 
@@ -223,20 +242,21 @@ static int seed_blocks(long n) {
 
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
                              float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
-                             int relu_tanh, float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
                              cudaStream_t stream) {
   IgrCfgDev c;
   c.mean_t_dev = mean_t_dev;
+  c.absmax = absmax;
   c.delta = delta; c.tau = tau; c.lambda_g = lambda_g; c.thr = thr; c.mean_t = mean_t;
-  c.inv_n = static_cast<float>(inv_n); c.data_term = data_term; c.relu_tanh = relu_tanh; c.seed_scale = seed_scale;
+  c.inv_n = static_cast<float>(inv_n); c.data_term = data_term; c.relu_tanh = relu_tanh;
   igr_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, y, n, c, fbar, gbar, sums);
   sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(fbar, n, fbar_sum);
   return cudaGetLastError();
 }
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
-                             float seed_scale, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
                              cudaStream_t stream) {
-  pcd_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, n, which, coef, relu_tanh, seed_scale, fbar, gbar, sums);
+  pcd_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, n, which, coef, relu_tanh, absmax, fbar, gbar, sums);
   sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(fbar, n, fbar_sum);
   return cudaGetLastError();
 }
@@ -258,6 +278,34 @@ __global__ void tanh_seeds_kernel(const float* __restrict__ f, const float* __re
 cudaError_t launch_tanh_seeds(const float* f, const float* g, const float* fbar_in, const float* gbar_in, int64_t n,
                               float* fbar, float* gbar, cudaStream_t stream) {
   tanh_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, fbar_in, gbar_in, n, fbar, gbar);
+  return cudaGetLastError();
+}
+// max |v| over a seed array (generic backward), and the power-of-two scale derived from it
+__global__ void absmax_kernel(const float* __restrict__ v, long n, unsigned* __restrict__ absmax) {
+  float m = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) m = fmaxf(m, fabsf(v[i]));
+  block_absmax(m, absmax);
+}
+// scale[0] = 2^-ceil(log2(absmax)) (largest seed lands in (0.5, 1]), scale[1] = 1 / scale[0]; absmax is reset
+__global__ void seed_scale_kernel(unsigned* __restrict__ absmax, float* __restrict__ scale) {
+  const float m = __uint_as_float(*absmax);
+  int e = 0;
+  float mult = 1.f;
+  if (m > 0.f) {
+    frexpf(m, &e);              // m = f * 2^e, f in [0.5, 1)
+    e = e > 120 ? 120 : (e < -120 ? -120 : e);
+    mult = ldexpf(1.f, -e);
+  }
+  scale[0] = mult;
+  scale[1] = 1.f / mult;
+  *absmax = 0u;
+}
+cudaError_t launch_absmax(const float* v, int64_t n, unsigned* absmax, cudaStream_t stream) {
+  absmax_kernel<<<seed_blocks(n), 256, 0, stream>>>(v, n, absmax);
+  return cudaGetLastError();
+}
+cudaError_t launch_seed_scale(unsigned* absmax, float* scale, cudaStream_t stream) {
+  seed_scale_kernel<<<1, 1, 0, stream>>>(absmax, scale);
   return cudaGetLastError();
 }
 cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream) {

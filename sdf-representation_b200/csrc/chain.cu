@@ -1,4 +1,4 @@
-// Layer-chain kernel: one persistent CTA per SM walks 128-point tiles through a *program* of layer GEMMs
+// Layer-chain kernel: one persistent CTA per SM walks point tiles through a *program* of layer GEMMs
 // (tcgen05.mma, fp32 accumulators in TMEM) whose epilogues apply the activation / derivative math and write
 // the next A operand straight back into shared memory, so point activations never leave the SM inside a sweep.
 //
@@ -11,8 +11,14 @@
 // State that must survive between sweeps (a_l, q_l, adot_l, u_l, Zbar_l) is spilled as operand images that the
 // weight-gradient kernel (dw.cu) consumes directly.
 //
+// Two precision modes (template parameter PAR):
+//   fast   : tile = 128 points, one 16-bit operand per value, one MMA pass             (error ~ 2^-11 relative)
+//   parity : tile = 64 points; image rows 0-63 hold hi = rnd16(v), rows 64-127 hold lo = rnd16(v - hi); the weight
+//            stream carries W_hi chunks then W_lo chunks.  One M=128 accumulator then holds v_hi.(W_hi+W_lo) in lanes
+//            0-63 and v_lo.(W_hi+W_lo) in lanes 64-127; the epilogue adds the two lane halves (fp32-grade result).
+//
 // Warp roles (320 threads): warps 0-7 epilogue (warp e owns TMEM lanes 32*(e%4).., columns half e/4 of each
-// 64-column block), warp 8 weight producer (cp.async.bulk into a 3-stage ring), warp 9 MMA issuer.
+// 64-column block), warp 8 weight producer (cp.async.bulk into a ring), warp 9 MMA issuer.
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cstdio>
@@ -21,11 +27,20 @@
 
 namespace sdf {
 
-constexpr int kNumStages = 3;
 constexpr int kEpiThreads = 256;
 constexpr int kChainThreads = 320;
 constexpr uint32_t kABytes = kMaxH / 8 * kGranuleBytes;  // 131072
-constexpr uint32_t kChainSmem = kABytes + kNumStages * kStageBytes + 128 /*barriers*/ + kTileRows * 3 * 4 /*gskip*/;
+constexpr uint32_t kScratchBytes = 2 * 32 * kParityPoints * 4;  // parity: lane-half exchange, [h][32 cols][64 points] fp32
+
+template <bool PAR>
+struct ChainCfg {
+  static constexpr int kStages = PAR ? 2 : 3;
+  static constexpr int kPoints = PAR ? kParityPoints : kTileRows;
+  static constexpr uint32_t kBarOff = kABytes + kStages * kStageBytes;
+  static constexpr uint32_t kGskipOff = kBarOff + 128;
+  static constexpr uint32_t kScratchOff = kGskipOff + kTileRows * 3 * 4;
+  static constexpr uint32_t kSmem = kScratchOff + (PAR ? kScratchBytes : 0);
+};
 
 template <int DT>
 struct H16;
@@ -76,6 +91,14 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   t = H16<DT>::unpack(u.z); v[4] = t.x; v[5] = t.y;
   t = H16<DT>::unpack(u.w); v[6] = t.x; v[7] = t.y;
 }
+template <int DT>
+__device__ __forceinline__ void unpack8_add(const uint4& u, float* v) {
+  float2 t;
+  t = H16<DT>::unpack(u.x); v[0] += t.x; v[1] += t.y;
+  t = H16<DT>::unpack(u.y); v[2] += t.x; v[3] += t.y;
+  t = H16<DT>::unpack(u.z); v[4] += t.x; v[5] += t.y;
+  t = H16<DT>::unpack(u.w); v[6] += t.x; v[7] += t.y;
+}
 
 // Split a float into three 16-bit terms hi + lo + lolo (exact to ~fp32 for bf16, beyond for fp16).
 template <int DT>
@@ -103,8 +126,10 @@ __device__ __forceinline__ float act_em(float a, float beta, bool relu) {
 struct Epi {
   uint32_t sA;      // shared address of the A image
   uint32_t taddr;   // TMEM base + this warp's lane quarter
-  int row;          // tile row == TMEM lane
+  int prow;         // point row inside the tile (image row of the hi / only copy)
   int h;            // column half within each 64-column block
+  bool math;        // fast: always; parity: warps holding the hi lanes do the arithmetic, the others ferry lanes 64-127
+  float* scr;       // parity: exchange buffer of this thread's column-half group, [32][64]
   int64_t grow;     // global point index
   bool valid;
   size_t tile;
@@ -113,31 +138,54 @@ struct Epi {
   float fval;       // network output of this row (kept for the tanh mode)
 };
 
-template <int DT>
+__device__ __forceinline__ uint32_t img_off(int c0, int j, int row) {
+  return static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + row * 16;
+}
+
+// 32 columns of this thread's point -> A image in shared memory and / or a spill image in global memory
+template <int DT, bool PAR>
 __device__ __forceinline__ void store_chunk(const Epi& e, int c0, const float (&v)[32], uint8_t* img, bool to_smem) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    uint4 pk = pack8<DT>(&v[8 * j]);
-    uint32_t off = static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + e.row * 16;
-    if (to_smem) st_smem_v4(e.sA + off, pk);
-    if (img) *reinterpret_cast<uint4*>(img + off) = pk;
+    if (!PAR) {
+      const uint4 pk = pack8<DT>(&v[8 * j]);
+      const uint32_t off = img_off(c0, j, e.prow);
+      if (to_smem) st_smem_v4(e.sA + off, pk);
+      if (img) *reinterpret_cast<uint4*>(img + off) = pk;
+    } else {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        hi[t] = H16<DT>::rnd(v[8 * j + t]);
+        lo[t] = v[8 * j + t] - hi[t];
+      }
+      const uint4 ph = pack8<DT>(hi), pl = pack8<DT>(lo);
+      const uint32_t oh = img_off(c0, j, e.prow), ol = img_off(c0, j, e.prow + kParityPoints);
+      if (to_smem) { st_smem_v4(e.sA + oh, ph); st_smem_v4(e.sA + ol, pl); }
+      if (img) { *reinterpret_cast<uint4*>(img + oh) = ph; *reinterpret_cast<uint4*>(img + ol) = pl; }
+    }
   }
 }
-template <int DT>
+template <int DT, bool PAR>
 __device__ __forceinline__ void load_chunk_global(const Epi& e, int c0, const uint8_t* img, float (&v)[32]) {
-  uint4 pk[4];
+  uint4 pk[4], pl[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    pk[j] = *reinterpret_cast<const uint4*>(img + static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + e.row * 16);
+  for (int j = 0; j < 4; ++j) {
+    pk[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow));
+    if (PAR) pl[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow + kParityPoints));
+  }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) unpack8<DT>(pk[j], &v[8 * j]);
+  for (int j = 0; j < 4; ++j) {
+    unpack8<DT>(pk[j], &v[8 * j]);
+    if (PAR) unpack8_add<DT>(pl[j], &v[8 * j]);
+  }
 }
-template <int DT>
+template <int DT, bool PAR>
 __device__ __forceinline__ void load_chunk_smem(const Epi& e, int c0, float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    uint4 pk = ld_smem_v4(e.sA + static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + e.row * 16);
-    unpack8<DT>(pk, &v[8 * j]);
+    unpack8<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow)), &v[8 * j]);
+    if (PAR) unpack8_add<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow + kParityPoints)), &v[8 * j]);
   }
 }
 __device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&b)[32]) {
@@ -147,12 +195,28 @@ __device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&
     b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
   }
 }
+// 32 accumulator columns of this thread's point.  Parity: every thread of the column-half group must call (the
+// threads of lanes 64-127 hand their half over through shared memory); only e.math threads get a result.
+template <bool PAR>
 __device__ __forceinline__ void load_acc32(const Epi& e, int c0, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32(e.taddr + c0, r);
   tmem_ld_wait();
+  if (!PAR) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  } else {
+    if (!e.math) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) e.scr[j * kParityPoints + e.prow] = __uint_as_float(r[j]);
+    }
+    named_bar_sync(2 + e.h, 128);
+    if (e.math) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + e.scr[j * kParityPoints + e.prow];
+    }
+    named_bar_sync(2 + e.h, 128);
+  }
 }
 
 __device__ __forceinline__ uint8_t* img_ptr(uint8_t* base, int layer, int n_tiles, size_t tile, uint32_t ib) {
@@ -175,24 +239,43 @@ __device__ __forceinline__ uint4 xblock_granule(const float (&x)[3], int h, floa
   return pack8<DT>(v);
 }
 
-template <int DT>
+// write granule e.h of a 16-column block for this thread's point (parity: the lo row of a block is zero, the split
+// lives in the columns) into shared memory and / or global memory
+template <bool PAR>
+__device__ __forceinline__ void put_block(const Epi& e, const uint4& g, bool to_smem, uint8_t* gimg) {
+  const uint32_t off = e.h * kGranuleBytes + e.prow * 16;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  if (to_smem) {
+    st_smem_v4(e.sA + off, g);
+    if (PAR) st_smem_v4(e.sA + off + kParityPoints * 16, z);
+  }
+  if (gimg) {
+    *reinterpret_cast<uint4*>(gimg + off) = g;
+    if (PAR) *reinterpret_cast<uint4*>(gimg + off + kParityPoints * 16) = z;
+  }
+}
+
+template <int DT, bool PAR>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
+  using Cfg = ChainCfg<PAR>;
+  constexpr int NST = Cfg::kStages;
+  constexpr int PTS = Cfg::kPoints;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kNumStages * kStageBytes);
-  uint64_t* w_full = bars;                  // [kNumStages]
-  uint64_t* w_empty = bars + kNumStages;    // [kNumStages]
-  uint64_t* acc_full = bars + 2 * kNumStages;
-  uint64_t* a_ready = bars + 2 * kNumStages + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 2);
-  float* gskip = reinterpret_cast<float*>(smem + kABytes + kNumStages * kStageBytes + 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* w_full = bars;            // [NST]
+  uint64_t* w_empty = bars + NST;     // [NST]
+  uint64_t* acc_full = bars + 2 * NST;
+  uint64_t* a_ready = bars + 2 * NST + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2);
+  float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumStages; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
@@ -222,7 +305,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             mbar_arrive_expect_tx(&w_full[stage], st.chunk_bytes);
             bulk_g2s(sW + stage * kStageBytes, src + static_cast<size_t>(c) * st.chunk_bytes, st.chunk_bytes,
                      &w_full[stage]);
-            if (++stage == kNumStages) { stage = 0; ++round; }
+            if (++stage == NST) { stage = 0; ++round; }
           }
         }
       }
@@ -244,7 +327,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             for (int kc = 0; kc < st.kchunks; ++kc) {
               mbar_wait(&w_full[stage], round & 1);
               tc_fence_after();
-              const uint32_t a_addr = sA_u + static_cast<uint32_t>(kc * st.k16 * 2) * kGranuleBytes;
+              const uint32_t a_addr = sA_u + static_cast<uint32_t>((kc % st.a_chunks) * st.k16 * 2) * kGranuleBytes;
               const uint32_t b_addr = sW_u + stage * kStageBytes;
               for (int k = 0; k < st.k16; ++k) {
                 const uint64_t da = make_smem_desc(a_addr + k * 2 * kGranuleBytes, kGranuleBytes, 128);
@@ -252,7 +335,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                 umma_f16_ss(tmem_base + g * st.ng, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
               }
               umma_commit(&w_empty[stage]);
-              if (++stage == kNumStages) { stage = 0; ++round; }
+              if (++stage == NST) { stage = 0; ++round; }
             }
           }
           umma_commit(acc_full);
@@ -266,76 +349,84 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     e.sA = smem_u32(sA);
     const int q = warp & 3;
     e.h = warp >> 2;
-    e.row = q * 32 + lane;
+    e.math = !PAR || q < 2;
+    e.prow = PAR ? (q & 1) * 32 + lane : q * 32 + lane;
+    e.scr = reinterpret_cast<float*>(smem + Cfg::kScratchOff) + e.h * 32 * kParityPoints;
     e.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     e.fval = 0.f;
     e.fb = 0.f;
     uint32_t gemm = 0;
     const int nIt = p.H / 64;
     const float beta = p.beta, inv_beta = p.inv_beta;
+    const float mult = p.seed_mult ? __ldg(p.seed_mult) : 1.f;
+    // layer whose image carries the raw input in its last three columns (feeds the skip layer): those columns have no
+    // activation state, their derivative factor must read as 0 (and exp(-beta x) may overflow for x < 0)
+    const int inj_layer = p.skip > 0 ? p.skip - 1 : -1;
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       e.tile = tile;
-      e.grow = static_cast<int64_t>(tile) * kTileRows + e.row;
+      e.grow = static_cast<int64_t>(tile) * PTS + e.prow;
       e.valid = e.grow < p.n;
       // ---------------------------------------------------------------- prologue: input block
       const int first = p.steps[0].epi;
       e.x[0] = e.x[1] = e.x[2] = 0.f;
       if (first == EPI_FWD_HIDDEN) {
-        if (e.valid) {
-          if (p.src == SRC_POINTS) {
-            e.x[0] = __ldg(p.x + e.grow * 3 + 0);
-            e.x[1] = __ldg(p.x + e.grow * 3 + 1);
-            e.x[2] = __ldg(p.x + e.grow * 3 + 2);
-          } else if (p.src == SRC_GRID) {
-            // reference executor/executor.py:351-356: coords = stack(meshgrid(x,x,x,'ij'),-1).reshape(-1,3)
-            const int64_t idx = p.grid_off + e.grow;
-            const int64_t nn = p.grid_n;
-            const int iz = static_cast<int>(idx % nn);
-            const int iy = static_cast<int>((idx / nn) % nn);
-            const int ix = static_cast<int>(idx / (nn * nn));
-            e.x[0] = __ldg(p.axis + ix);
-            e.x[1] = __ldg(p.axis + iy);
-            e.x[2] = __ldg(p.axis + iz);
-          } else {
-            // octree cell centre from a 3x21-bit Morton key at the given level: c = -1 + (2 i + 1) * 2^-level
-            const uint64_t key = __ldg(p.keys + e.grow);
-            uint32_t ci[3] = {0, 0, 0};
-            for (int b = 0; b < p.level; ++b) {
-              ci[0] |= static_cast<uint32_t>((key >> (3 * b + 2)) & 1) << b;
-              ci[1] |= static_cast<uint32_t>((key >> (3 * b + 1)) & 1) << b;
-              ci[2] |= static_cast<uint32_t>((key >> (3 * b + 0)) & 1) << b;
-            }
-            const float hs = ldexpf(1.f, -p.level);
+        if (e.math) {
+          if (e.valid) {
+            if (p.src == SRC_POINTS) {
+              e.x[0] = __ldg(p.x + e.grow * 3 + 0);
+              e.x[1] = __ldg(p.x + e.grow * 3 + 1);
+              e.x[2] = __ldg(p.x + e.grow * 3 + 2);
+            } else if (p.src == SRC_GRID) {
+              // reference executor/executor.py:351-356: coords = stack(meshgrid(x,x,x,'ij'),-1).reshape(-1,3)
+              const int64_t idx = p.grid_off + e.grow;
+              const int64_t nn = p.grid_n;
+              const int iz = static_cast<int>(idx % nn);
+              const int iy = static_cast<int>((idx / nn) % nn);
+              const int ix = static_cast<int>(idx / (nn * nn));
+              e.x[0] = __ldg(p.axis + ix);
+              e.x[1] = __ldg(p.axis + iy);
+              e.x[2] = __ldg(p.axis + iz);
+            } else {
+              // octree cell centre from a 3-bit-per-level Morton key: c = -1 + (2 i + 1) * 2^-level
+              const uint64_t key = __ldg(p.keys + e.grow);
+              uint32_t ci[3] = {0, 0, 0};
+              for (int b = 0; b < p.level; ++b) {
+                ci[0] |= static_cast<uint32_t>((key >> (3 * b + 2)) & 1) << b;
+                ci[1] |= static_cast<uint32_t>((key >> (3 * b + 1)) & 1) << b;
+                ci[2] |= static_cast<uint32_t>((key >> (3 * b + 0)) & 1) << b;
+              }
+              const float hs = ldexpf(1.f, -p.level);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) e.x[j] = -1.f + (2.f * static_cast<float>(ci[j]) + 1.f) * hs;
+              for (int j = 0; j < 3; ++j) e.x[j] = -1.f + (2.f * static_cast<float>(ci[j]) + 1.f) * hs;
+            }
           }
+          const uint4 gx = xblock_granule<DT>(e.x, e.h, 1.f);
+          put_block<PAR>(e, gx, true,
+                         (p.flags & FL_SPILL_X) ? p.Ximg + tile * static_cast<size_t>(2 * kGranuleBytes) : nullptr);
         }
-        const uint4 gx = xblock_granule<DT>(e.x, e.h, 1.f);
-        st_smem_v4(e.sA + e.h * kGranuleBytes + e.row * 16, gx);
-        if (p.flags & FL_SPILL_X)
-          *reinterpret_cast<uint4*>(p.Ximg + tile * static_cast<size_t>(2 * kGranuleBytes) + e.h * kGranuleBytes + e.row * 16) = gx;
       } else {
         // tangent / adjoint program: seeds
-        if (e.valid) {
-          e.fb = p.fbar ? __ldg(p.fbar + e.grow) : 0.f;
-          if (p.gbar) {
-            e.x[0] = __ldg(p.gbar + e.grow * 3 + 0);
-            e.x[1] = __ldg(p.gbar + e.grow * 3 + 1);
-            e.x[2] = __ldg(p.gbar + e.grow * 3 + 2);
+        if (e.math) {
+          if (e.valid) {
+            e.fb = p.fbar ? __ldg(p.fbar + e.grow) * mult : 0.f;
+            if (p.gbar) {
+              e.x[0] = __ldg(p.gbar + e.grow * 3 + 0) * mult;
+              e.x[1] = __ldg(p.gbar + e.grow * 3 + 1) * mult;
+              e.x[2] = __ldg(p.gbar + e.grow * 3 + 2) * mult;
+            }
+          } else {
+            e.fb = 0.f;
           }
-        } else {
-          e.fb = 0.f;
+          const uint4 gg = xblock_granule<DT>(e.x, e.h, 0.f);
+          put_block<PAR>(e, gg, true, p.Gimg + tile * static_cast<size_t>(2 * kGranuleBytes));
+          // f-bar block: cols 0-2 = fbar hi/lo/lolo, col 15 = 1
+          float fh, fl, fll;
+          split3<DT>(e.fb, fh, fl, fll);
+          float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (e.h == 0) { sv[0] = fh; sv[1] = fl; sv[2] = fll; } else { sv[7] = e.valid ? 1.f : 0.f; }
+          put_block<PAR>(e, pack8<DT>(sv), false, p.Simg + tile * static_cast<size_t>(2 * kGranuleBytes));
         }
-        const uint4 gg = xblock_granule<DT>(e.x, e.h, 0.f);
-        st_smem_v4(e.sA + e.h * kGranuleBytes + e.row * 16, gg);
-        *reinterpret_cast<uint4*>(p.Gimg + tile * static_cast<size_t>(2 * kGranuleBytes) + e.h * kGranuleBytes + e.row * 16) = gg;
-        // f-bar block: cols 0-2 = fbar hi/lo/lolo, col 15 = 1
-        float fh, fl, fll;
-        split3<DT>(e.fb, fh, fl, fll);
-        float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (e.h == 0) { sv[0] = fh; sv[1] = fl; sv[2] = fll; } else { sv[7] = 1.f; }
-        *reinterpret_cast<uint4*>(p.Simg + tile * static_cast<size_t>(2 * kGranuleBytes) + e.h * kGranuleBytes + e.row * 16) = pack8<DT>(sv);
       }
       fence_proxy_async_smem();
 
@@ -352,41 +443,47 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         switch (st.epi) {
           case EPI_FWD_HIDDEN: {
             uint8_t* aimg = (p.flags & FL_SPILL_A) ? img_ptr(p.Aimg, l, p.n_tiles, tile, ib) : nullptr;
-            const bool inject = (p.skip > 0) && (l + 1 == p.skip);
+            const bool inject = l == inj_layer;
             for (int it = 0; it < nIt; ++it) {
               const int c0 = it * 64 + e.h * 32;
-              float v[32], b[32];
-              load_vec32(p.bias + l * p.H + c0, b);
-              load_acc32(e, c0, v);
+              float v[32];
+              load_acc32<PAR>(e, c0, v);
+              if (e.math) {
+                float b[32];
+                load_vec32(p.bias + l * p.H + c0, b);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j] + b[j], beta, inv_beta, relu);
-              if (inject && c0 + 32 == p.H) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }
-              store_chunk<DT>(e, c0, v, aimg, true);
+                for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j] + b[j], beta, inv_beta, relu);
+                if (inject && c0 + 32 == p.H) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }
+                store_chunk<DT, PAR>(e, c0, v, aimg, true);
+              }
             }
             fence_proxy_async_smem();
           } break;
           case EPI_FWD_LAST: {
             if (e.h == 0) {
-              uint32_t r[16];
-              tmem_ld16(e.taddr, r);
-              tmem_ld_wait();
-              float z = __uint_as_float(r[0]) + __ldg(p.bias + l * p.H);
-              // reference model/networks.py:104-105: tanh on the output when the activation is ReLU
-              e.fval = relu ? tanhf(z) : z;
-              if (e.valid && p.f_out) p.f_out[e.grow] = e.fval;
+              float v[32];
+              load_acc32<PAR>(e, 0, v);
+              if (e.math) {
+                const float z = v[0] + __ldg(p.bias + l * p.H);
+                // reference model/networks.py:104-105: tanh on the output when the activation is ReLU
+                e.fval = relu ? tanhf(z) : z;
+                if (e.valid && p.f_out) p.f_out[e.grow] = e.fval;
+              }
             }
           } break;
           case EPI_REV_START: {
             // q_{L-1} = w_L * act'(z_{L-1}); the A image still holds a_{L-1}
             uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l, p.n_tiles, tile, ib) : nullptr;
-            for (int it = 0; it < nIt; ++it) {
-              const int c0 = it * 64 + e.h * 32;
-              float a[32], w[32];
-              load_vec32(p.w_last + c0, w);
-              load_chunk_smem<DT>(e, c0, a);
+            if (e.math) {
+              for (int it = 0; it < nIt; ++it) {
+                const int c0 = it * 64 + e.h * 32;
+                float a[32], w[32];
+                load_vec32(p.w_last + c0, w);
+                load_chunk_smem<DT, PAR>(e, c0, a);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) a[j] = w[j] * (1.f - act_em(a[j], beta, relu));
-              store_chunk<DT>(e, c0, a, qimg, true);
+                for (int j = 0; j < 32; ++j) a[j] = w[j] * (1.f - act_em(a[j], beta, relu));
+                store_chunk<DT, PAR>(e, c0, a, qimg, true);
+              }
             }
             fence_proxy_async_smem();
           } break;
@@ -394,41 +491,46 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             // GEMM r = q_l W_l done; q_{l-1} = r * act'(z_{l-1});  l = st.layer
             const uint8_t* aimg = img_ptr(p.Aimg, l - 1, p.n_tiles, tile, ib);
             uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l - 1, p.n_tiles, tile, ib) : nullptr;
-            const bool is_skip = (p.skip > 0) && (l == p.skip);
+            const bool is_skip = (l - 1) == inj_layer;
             for (int it = 0; it < nIt; ++it) {
               const int c0 = it * 64 + e.h * 32;
-              float v[32], a[32];
-              load_chunk_global<DT>(e, c0, aimg, a);
-              load_acc32(e, c0, v);
-              if (is_skip && c0 + 32 == p.H) {
-                // rows H-3..H-1 of W_skip multiply the raw input: their product is d f / d x through the skip
-                gskip[e.row * 3 + 0] = v[29]; gskip[e.row * 3 + 1] = v[30]; gskip[e.row * 3 + 2] = v[31];
-                v[29] = v[30] = v[31] = 0.f;
-              }
+              float v[32];
+              load_acc32<PAR>(e, c0, v);
+              if (e.math) {
+                float a[32];
+                load_chunk_global<DT, PAR>(e, c0, aimg, a);
+                if (is_skip && c0 + 32 == p.H) {
+                  // rows H-3..H-1 of W_skip multiply the raw input: their product is d f / d x through the skip
+                  gskip[e.prow * 3 + 0] = v[29]; gskip[e.prow * 3 + 1] = v[30]; gskip[e.prow * 3 + 2] = v[31];
+                  a[29] = a[30] = a[31] = 0.f;
+                }
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = v[j] * (1.f - act_em(a[j], beta, relu));
-              store_chunk<DT>(e, c0, v, qimg, true);
+                for (int j = 0; j < 32; ++j) v[j] = v[j] * (1.f - act_em(a[j], beta, relu));
+                store_chunk<DT, PAR>(e, c0, v, qimg, true);
+              }
             }
             fence_proxy_async_smem();
           } break;
           case EPI_REV_LAST: {
             named_bar_sync(1, kEpiThreads);  // gskip written by the h=1 warps of an earlier step
             if (e.h == 0) {
-              uint32_t r[16];
-              tmem_ld16(e.taddr, r);
-              tmem_ld_wait();
-              float g[3];
+              float v[32];
+              load_acc32<PAR>(e, 0, v);
+              if (e.math) {
+                float g[3];
 #pragma unroll
-              for (int j = 0; j < 3; ++j) g[j] = __uint_as_float(r[j]) + (p.skip > 0 ? gskip[e.row * 3 + j] : 0.f);
-              if (relu) {
-                const float d = 1.f - e.fval * e.fval;  // d tanh
+                for (int j = 0; j < 3; ++j) g[j] = v[j] + (p.skip > 0 ? gskip[e.prow * 3 + j] : 0.f);
+                if (relu) {
+                  const float d = 1.f - e.fval * e.fval;  // d tanh
 #pragma unroll
-                for (int j = 0; j < 3; ++j) g[j] *= d;
-              }
-              if (e.valid && p.g_out) {
-                p.g_out[e.grow * 3 + 0] = g[0]; p.g_out[e.grow * 3 + 1] = g[1]; p.g_out[e.grow * 3 + 2] = g[2];
+                  for (int j = 0; j < 3; ++j) g[j] *= d;
+                }
+                if (e.valid && p.g_out) {
+                  p.g_out[e.grow * 3 + 0] = g[0]; p.g_out[e.grow * 3 + 1] = g[1]; p.g_out[e.grow * 3 + 2] = g[2];
+                }
               }
             }
+            named_bar_sync(1, kEpiThreads);  // gskip may be rewritten by the next tile
           } break;
           case EPI_TAN_HIDDEN: {
             // zdot_l in TMEM;  adot_l = s' zdot_l -> next A;  u_l = beta (1-s') q_l zdot_l
@@ -436,25 +538,29 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             const uint8_t* qimg = img_ptr(p.Qimg, l, p.n_tiles, tile, ib);
             uint8_t* adimg = img_ptr(p.ADimg, l, p.n_tiles, tile, ib);
             uint8_t* uimg = relu ? nullptr : img_ptr(p.Uimg, l, p.n_tiles, tile, ib);
-            const bool inject = (p.skip > 0) && (l + 1 == p.skip);
+            const bool inject = l == inj_layer;
             for (int it = 0; it < nIt; ++it) {
               const int c0 = it * 64 + e.h * 32;
-              float zd[32], a[32];
-              load_chunk_global<DT>(e, c0, aimg, a);
-              load_acc32(e, c0, zd);
+              float zd[32];
+              load_acc32<PAR>(e, c0, zd);
+              if (e.math) {
+                float a[32];
+                load_chunk_global<DT, PAR>(e, c0, aimg, a);
+                if (inject && c0 + 32 == p.H) a[29] = a[30] = a[31] = 0.f;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) a[j] = act_em(a[j], beta, relu);  // a := 1 - s'
-              if (!relu) {
-                float qv[32];
-                load_chunk_global<DT>(e, c0, qimg, qv);
+                for (int j = 0; j < 32; ++j) a[j] = act_em(a[j], beta, relu);  // a := 1 - s'
+                if (!relu) {
+                  float qv[32];
+                  load_chunk_global<DT, PAR>(e, c0, qimg, qv);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) qv[j] = beta * a[j] * qv[j] * zd[j];
-                store_chunk<DT>(e, c0, qv, uimg, false);
+                  for (int j = 0; j < 32; ++j) qv[j] = beta * a[j] * qv[j] * zd[j];
+                  store_chunk<DT, PAR>(e, c0, qv, uimg, false);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) zd[j] = (1.f - a[j]) * zd[j];
+                if (inject && c0 + 32 == p.H) { zd[29] = e.x[0]; zd[30] = e.x[1]; zd[31] = e.x[2]; }
+                store_chunk<DT, PAR>(e, c0, zd, adimg, true);
               }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) zd[j] = (1.f - a[j]) * zd[j];
-              if (inject && c0 + 32 == p.H) { zd[29] = e.x[0]; zd[30] = e.x[1]; zd[31] = e.x[2]; }
-              store_chunk<DT>(e, c0, zd, adimg, true);
             }
             fence_proxy_async_smem();
           } break;
@@ -464,20 +570,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             const bool has_u = (p.flags & FL_TANGENT) && !relu;
             const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
             uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
-            for (int it = 0; it < nIt; ++it) {
-              const int c0 = it * 64 + e.h * 32;
-              float a[32], w[32];
-              load_vec32(p.w_last + c0, w);
-              load_chunk_global<DT>(e, c0, aimg, a);
+            if (e.math) {
+              for (int it = 0; it < nIt; ++it) {
+                const int c0 = it * 64 + e.h * 32;
+                float a[32], w[32];
+                load_vec32(p.w_last + c0, w);
+                load_chunk_global<DT, PAR>(e, c0, aimg, a);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) a[j] = (1.f - act_em(a[j], beta, relu)) * (w[j] * e.fb);
-              if (has_u) {
-                float u[32];
-                load_chunk_global<DT>(e, c0, uimg, u);
+                for (int j = 0; j < 32; ++j) a[j] = (1.f - act_em(a[j], beta, relu)) * (w[j] * e.fb);
+                if (has_u) {
+                  float u[32];
+                  load_chunk_global<DT, PAR>(e, c0, uimg, u);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] += u[j];
+                  for (int j = 0; j < 32; ++j) a[j] += u[j];
+                }
+                store_chunk<DT, PAR>(e, c0, a, zimg, true);
               }
-              store_chunk<DT>(e, c0, a, zimg, true);
             }
             fence_proxy_async_smem();
           } break;
@@ -487,22 +595,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             const bool has_u = (p.flags & FL_TANGENT) && !relu;
             const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
             uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
-            const bool from_skip = (p.skip > 0) && (l + 1 == p.skip);
+            const bool from_skip = l == inj_layer;
             for (int it = 0; it < nIt; ++it) {
               const int c0 = it * 64 + e.h * 32;
-              float v[32], a[32];
-              load_chunk_global<DT>(e, c0, aimg, a);
-              load_acc32(e, c0, v);
-              if (from_skip && c0 + 32 == p.H) v[29] = v[30] = v[31] = 0.f;  // those rows fed the raw input
+              float v[32];
+              load_acc32<PAR>(e, c0, v);
+              if (e.math) {
+                float a[32];
+                load_chunk_global<DT, PAR>(e, c0, aimg, a);
+                if (from_skip && c0 + 32 == p.H) a[29] = a[30] = a[31] = 0.f;  // those rows fed the raw input
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (1.f - act_em(a[j], beta, relu)) * v[j];
-              if (has_u) {
-                float u[32];
-                load_chunk_global<DT>(e, c0, uimg, u);
+                for (int j = 0; j < 32; ++j) v[j] = (1.f - act_em(a[j], beta, relu)) * v[j];
+                if (has_u) {
+                  float u[32];
+                  load_chunk_global<DT, PAR>(e, c0, uimg, u);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += u[j];
+                  for (int j = 0; j < 32; ++j) v[j] += u[j];
+                }
+                store_chunk<DT, PAR>(e, c0, v, zimg, true);
               }
-              store_chunk<DT>(e, c0, v, zimg, true);
             }
             fence_proxy_async_smem();
           } break;
@@ -520,18 +631,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_chain(const ChainParams& p, int dtype, int num_sms, cudaStream_t stream) {
-  static bool attr_set[2] = {false, false};
-  auto kfn = dtype == DT_BF16 ? chain_kernel<DT_BF16> : chain_kernel<DT_FP16>;
-  if (!attr_set[dtype]) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kChainSmem));
+template <int DT, bool PAR>
+static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kfn = chain_kernel<DT, PAR>;
+  constexpr uint32_t smem = ChainCfg<PAR>::kSmem;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    attr_set[dtype] = true;
+    attr_set = true;
   }
-  if (p.n_tiles <= 0) return cudaSuccess;
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-  kfn<<<grid, kChainThreads, kChainSmem, stream>>>(p);
+  kfn<<<grid, kChainThreads, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int num_sms, cudaStream_t stream) {
+  if (p.n_tiles <= 0) return cudaSuccess;
+  if (dtype == DT_BF16) return parity ? launch_one<DT_BF16, true>(p, num_sms, stream) : launch_one<DT_BF16, false>(p, num_sms, stream);
+  return parity ? launch_one<DT_FP16, true>(p, num_sms, stream) : launch_one<DT_FP16, false>(p, num_sms, stream);
 }
 
 }  // namespace sdf

@@ -22,7 +22,7 @@ constexpr uint32_t kDwStageBytes = kDwABytes + kDwBBytes;
 constexpr uint32_t kDwSmem = kDwStages * kDwStageBytes + 128;
 
 template <int DT>
-__global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restrict__ items, int n_items, int swap_lbo_sbo) {
+__global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * kDwStageBytes);
   uint64_t* full = bars;                    // [2]
@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
   } else if (warp == 5) {
     if (lane == 0) {
       uint32_t stage = 0, round = 0, item_cnt = 0;
-      const uint32_t lbo = swap_lbo_sbo ? kGranuleBytes : 128u;   // K-group (8 points) stride
-      const uint32_t sbo = swap_lbo_sbo ? 128u : kGranuleBytes;   // MN-block (8 features) stride
+      const uint32_t lbo = 128u;            // K-group (8 image rows) stride
+      const uint32_t sbo = kGranuleBytes;   // MN-block (8 features) stride
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_cnt) {
         const DwItem d = items[it];
         const uint32_t as = item_cnt & 1;
@@ -87,12 +87,28 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * kDwStageBytes);
             const uint32_t b_addr = a_addr + kDwABytes;
+            if (!parity) {
 #pragma unroll
-            for (int k = 0; k < kTileRows / 16; ++k) {
-              const uint64_t da = make_smem_desc(a_addr + k * 256, lbo, sbo);
-              const uint64_t db = make_smem_desc(b_addr + k * 256, lbo, sbo);
-              umma_f16_ss(tmem_base + as * 256, da, db, idesc, first ? 0u : 1u);
-              first = 0;
+              for (int k = 0; k < kTileRows / 16; ++k) {
+                const uint64_t da = make_smem_desc(a_addr + k * 256, lbo, sbo);
+                const uint64_t db = make_smem_desc(b_addr + k * 256, lbo, sbo);
+                umma_f16_ss(tmem_base + as * 256, da, db, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            } else {
+              // image rows 0-63 = hi parts, 64-127 = lo parts of the same 64 points: hi.hi + lo.hi + hi.lo
+              // (lo.lo is below fp32 resolution)
+#pragma unroll
+              for (int k = 0; k < kParityPoints / 16; ++k) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  const uint32_t ka = k + (c == 1 ? 4 : 0), kb = k + (c == 2 ? 4 : 0);
+                  const uint64_t da = make_smem_desc(a_addr + ka * 256, lbo, sbo);
+                  const uint64_t db = make_smem_desc(b_addr + kb * 256, lbo, sbo);
+                  umma_f16_ss(tmem_base + as * 256, da, db, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+              }
             }
             umma_commit(&empty[stage]);
             if (++stage == kDwStages) { stage = 0; ++round; }
@@ -111,12 +127,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
       mbar_wait(&acc_full[as], (item_cnt >> 1) & 1);
       tc_fence_after();
       if (d.tile1 > d.tile0) {
+        const float im = d.inv_mult ? __ldg(d.inv_mult) : 1.f;
         for (uint32_t c0 = 0; c0 < d.n; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(lane_addr + as * 256 + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(d.out + static_cast<size_t>(c0 + j) * d.out_ld + m, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j) atomicAdd(d.out + static_cast<size_t>(c0 + j) * d.out_ld + m, __uint_as_float(r[j]) * im);
         }
       }
       tc_fence_before();
@@ -128,13 +145,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
   if (warp == 5) tmem_dealloc<512>(tmem_base);
 }
 
-cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int num_sms, cudaStream_t stream) {
+cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream) {
   static bool attr_set[2] = {false, false};
-  static int swap = -1;
-  if (swap < 0) {
-    const char* s = getenv("SDFNET_DW_SWAP");
-    swap = (s && s[0] == '1') ? 1 : 0;
-  }
   auto kfn = dtype == DT_BF16 ? dw_kernel<DT_BF16> : dw_kernel<DT_FP16>;
   if (!attr_set[dtype]) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDwSmem));
@@ -143,7 +155,7 @@ cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int num_s
   }
   if (n_items <= 0) return cudaSuccess;
   const int grid = n_items < num_sms ? n_items : num_sms;
-  kfn<<<grid, kDwThreads, kDwSmem, stream>>>(items_dev, n_items, swap);
+  kfn<<<grid, kDwThreads, kDwSmem, stream>>>(items_dev, n_items, parity);
   return cudaGetLastError();
 }
 

@@ -12,7 +12,8 @@
 
 namespace sdf {
 
-constexpr int kTileRows = 128;           // rows of one operand image (points per tile; 64 hi + 64 lo when split)
+constexpr int kTileRows = 128;           // rows of one operand image: 128 points (fast) or 64 hi + 64 lo rows (parity)
+constexpr int kParityPoints = 64;        // points per tile in parity mode
 constexpr int kGranuleBytes = kTileRows * 16;  // 2048: one 8-column granule of a tile image
 constexpr int kMaxH = 512;
 constexpr int kMaxLayers = 16;           // hidden layers
@@ -40,7 +41,8 @@ struct StepDesc {
   int32_t layer;        // meaning depends on epi (index of the layer whose activation state is touched)
   int32_t n_groups;     // TMEM column groups of this GEMM; 0 = element-wise step without GEMM
   int32_t ng;           // N (rows of the weight chunk) per group
-  int32_t kchunks;      // weight chunks per group
+  int32_t kchunks;      // weight chunks per group (parity mode: hi chunks then lo chunks)
+  int32_t a_chunks;     // distinct A chunks; the A chunk of weight chunk kc is kc % a_chunks
   int32_t k16;          // K=16 instructions per chunk
   uint32_t chunk_bytes;
   uint32_t w_off;       // byte offset of the first chunk of this step in the packed weight stream
@@ -79,9 +81,11 @@ struct ChainParams {
   // outputs
   float* f_out;            // [n]
   float* g_out;            // [n][3]
-  // seeds (TA kernel)
+  // seeds (TA kernel); both are multiplied by *seed_mult (a power of two chosen so that the largest seed is O(1):
+  // keeps the 16-bit adjoint images out of fp16 subnormals), dw.cu multiplies the result by 1 / *seed_mult
   const float* fbar;       // [n]
   const float* gbar;       // [n][3]
+  const float* seed_mult;  // device scalar, may be nullptr (= 1)
   // spill images, each [layer][tile][image]
   uint8_t* Aimg;
   uint8_t* Qimg;
@@ -106,6 +110,7 @@ struct DwItem {
   uint32_t tile0, tile1;
   uint32_t out_ld;                 // leading dimension (elements) of out (index [n][m])
   float* out;
+  const float* inv_mult;           // device scalar multiplied into the result (nullptr = 1)
 };
 
 __host__ __device__ inline uint32_t img_bytes(int H) { return static_cast<uint32_t>(H / 8) * kGranuleBytes; }

@@ -76,6 +76,23 @@ class Engine:
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ instrumentation
+    def launch_count(self):
+        """Kernels of libsdfnet.so launched through this engine so far (counted inside the library)."""
+        return int(self.lib.sdfnet_launch_count(self.handle))
+
+    def profile(self, on=True):
+        _lib.check(self.lib.sdfnet_profile_enable(self.handle, 1 if on else 0), "sdfnet_profile_enable")
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} measured with CUDA events on the launch stream."""
+        ms = (ctypes.c_double * 4)()
+        n = (ctypes.c_int64 * 4)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_profile_read(self.handle, ms, n), "sdfnet_profile_read")
+        names = ("chain_fwd_rev", "chain_tan_adj", "dw_gemm", "other")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}
+
     # ------------------------------------------------------------------ weights
     def pack(self, weights, biases, key=None):
         """Re-pack lin{i}.weight / lin{i}.bias into the UMMA operand images (skipped if ``key`` is unchanged)."""
