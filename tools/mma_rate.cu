@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int ts, int iters, 
       for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          if (ts) umma_f16_ts(tmem, tmem + 256 + k * 8, dbv[k], idesc, 1u);
-          else umma_f16_ss(tmem, dav[k], dbv[k], idesc, 1u);
+          // pre == 2: alternate between two accumulators (independent dependency chains)
+          const uint32_t d = tmem + ((pre == 2 && (k & 1)) ? static_cast<uint32_t>(N) : 0u);
+          if (ts) umma_f16_ts(d, tmem + 2 * N + k * 8, dbv[k], idesc, 1u);
+          else umma_f16_ss(d, dav[k], dbv[k], idesc, 1u);
         }
       }
     } else
