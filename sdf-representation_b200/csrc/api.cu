@@ -153,8 +153,8 @@ static StepImage make_image(int N, int K16total, int kchunk_k16, bool split, uin
 extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   if (!desc || !out) return fail(1, "sdfnet_create: null argument");
   if (desc->d_in != 3) return fail(1, "sdfnet_create: d_in must be 3 (got %d)", desc->d_in);
-  if (desc->hidden < 64 || desc->hidden > kMaxH || desc->hidden % 64)
-    return fail(1, "sdfnet_create: hidden width must be a multiple of 64 in [64,512] (got %d)", desc->hidden);
+  if (desc->hidden != 64 && desc->hidden != 128 && desc->hidden != 256 && desc->hidden != 512)
+    return fail(1, "sdfnet_create: hidden width must be 64, 128, 256 or 512 (got %d)", desc->hidden);
   if (desc->num_hidden < 2 || desc->num_hidden > kMaxLayers)
     return fail(1, "sdfnet_create: num_hidden must be in [2,%d] (got %d)", kMaxLayers, desc->num_hidden);
   if (desc->skip_layer < 0 || desc->skip_layer == 1 || desc->skip_layer >= desc->num_hidden)
@@ -289,6 +289,13 @@ static void add_step(ChainParams& p, int epi, int layer, const StepImage* img) {
   } else {
     s.n_groups = 0; s.ng = 0; s.kchunks = 0; s.k16 = 0; s.a_chunks = 1; s.chunk_bytes = 0; s.w_off = 0;
   }
+  // A columns [0,256) of a 512-wide image are released first (chain.cu hidden_step_staged)
+  s.k_lo = (img && img->a_chunks > 1 && img->k16 * 16 * img->a_chunks > 256) ? 256 / (img->k16 * 16) : 0;
+  s.signal = 0;
+}
+// a step's A image is consumed iff the next step of the program is a GEMM
+static void finish_program(ChainParams& p) {
+  for (int s = 0; s < p.n_steps; ++s) p.steps[s].signal = (s + 1 < p.n_steps && p.steps[s + 1].n_groups != 0) ? 1 : 0;
 }
 static void base_params(const sdfnet_handle* h, ChainParams& p) {
   memset(&p, 0, sizeof(p));
@@ -368,6 +375,7 @@ static int run_forward(sdfnet_t h, ChainParams& p, int64_t n, cudaStream_t strea
   p.n = n;
   p.n_tiles = static_cast<int>((n + h->pts - 1) / h->pts);
   prog_forward(h, p);
+  finish_program(p);
   Launch lr(h, PC_CHAIN_FG, stream);
   CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
   return 0;
@@ -458,6 +466,7 @@ extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float*
     p.flags |= FL_SPILL_A;
     prog_forward(h, p);
     prog_reverse(h, p);
+    finish_program(p);
     Launch lr(h, PC_CHAIN_FG, static_cast<cudaStream_t>(stream));
     CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, static_cast<cudaStream_t>(stream)));
   }
@@ -566,6 +575,7 @@ int run_fg(sdfnet_t h, const float* x, int64_t m, const Spill& s, bool need_g, c
   p.flags |= FL_SPILL_A | FL_SPILL_X | (need_g ? FL_SPILL_Q : 0u);
   prog_forward(h, p);
   if (need_g) prog_reverse(h, p);
+  finish_program(p);
   Launch lr(h, PC_CHAIN_FG, stream);
   CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
   return 0;
@@ -583,6 +593,7 @@ int run_ta(sdfnet_t h, int64_t m, const Spill& s, const float* fbar, const float
     prog_tangent(h, p);
   }
   prog_adjoint(h, p);
+  finish_program(p);
   Launch lr(h, PC_CHAIN_TA, stream);
   CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
   return 0;

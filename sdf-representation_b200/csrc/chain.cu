@@ -17,8 +17,9 @@
 //            stream carries W_hi chunks then W_lo chunks.  One M=128 accumulator then holds v_hi.(W_hi+W_lo) in lanes
 //            0-63 and v_lo.(W_hi+W_lo) in lanes 64-127; the epilogue adds the two lane halves (fp32-grade result).
 //
-// Warp roles (320 threads): warps 0-7 epilogue (warp e owns TMEM lanes 32*(e%4).., columns half e/4 of each
-// 64-column block), warp 8 weight producer (cp.async.bulk into a ring), warp 9 MMA issuer.
+// Warp roles (384 threads = 3 warpgroups; setmaxnreg moves registers from the third warpgroup to the epilogue warps):
+// warps 0-7 epilogue (warp e owns TMEM lanes 32*(e%4).., columns half e/4 of each
+// 64-column block), warp 8 weight producer (cp.async.bulk into a ring), warp 9 MMA issuer, warps 10-11 idle.
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cstdio>
@@ -28,7 +29,7 @@
 namespace sdf {
 
 constexpr int kEpiThreads = 256;
-constexpr int kChainThreads = 320;
+constexpr int kChainThreads = 384;  // 3 warpgroups: 2 x epilogue, 1 x {producer, MMA issuer, 2 idle warps}
 constexpr uint32_t kABytes = kMaxH / 8 * kGranuleBytes;  // 131072
 constexpr uint32_t kScratchBytes = 2 * 32 * kParityPoints * 4;  // parity: lane-half exchange, [h][32 cols][64 points] fp32
 
@@ -107,19 +108,6 @@ __device__ __forceinline__ void split3(float x, float& h, float& l, float& ll) {
   float r1 = x - h;
   l = H16<DT>::rnd(r1);
   ll = H16<DT>::rnd(r1 - l);
-}
-
-// act(z): torch.nn.Softplus(beta, threshold=20) / ReLU.  For beta*z > 20 the softplus expression below differs
-// from the reference's linear branch by < 2.1e-9/beta, far under fp32 resolution of z.
-__device__ __forceinline__ float act_fwd(float z, float beta, float inv_beta, bool relu) {
-  if (relu) return fmaxf(z, 0.f);
-  float e = __expf(-fabsf(beta * z));
-  return fmaxf(z, 0.f) + __logf(1.f + e) * inv_beta;
-}
-// exp(-beta*a) = 1 - sigmoid(beta z) recovered from the stored activation a = softplus(z); relu: [a <= 0].
-__device__ __forceinline__ float act_em(float a, float beta, bool relu) {
-  if (relu) return a > 0.f ? 0.f : 1.f;
-  return __expf(-beta * a);
 }
 
 // Per-thread epilogue context
@@ -255,6 +243,302 @@ __device__ __forceinline__ void put_block(const Epi& e, const uint4& g, bool to_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue building blocks
+// ------------------------------------------------------------------------------------------------
+struct Bars {
+  uint64_t* acc_full;  // [2]  MMA issuer -> epilogue: accumulator half g is complete
+  uint64_t* a_lo;      //      epilogue -> MMA issuer: A-image columns [0,256) (or all, H <= 256) are in place
+  uint64_t* a_hi;      //      epilogue -> MMA issuer: A-image columns [256,512) are in place
+};
+
+struct EpiConst {
+  int H;
+  float beta, inv_beta, nbl2, ln2_over_beta;  // nbl2 = -beta*log2(e)
+  bool relu;
+};
+
+// inputs / outputs of one step for this thread's tile
+struct StepIO {
+  const uint8_t* in_a;  // activation image whose act' multiplies the result (nullptr: forward)
+  const uint8_t* in_b;  // q image (tangent) or u image (adjoint); nullptr if absent
+  uint8_t* out;         // spill image of the result (nullptr: not spilled)
+  uint8_t* out_u;       // tangent: u image
+  const float* vec;     // forward: bias row
+  bool special;         // the last three columns of this layer carry the raw input (skip injection)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// softplus_beta(z) = max(z,0) + log1p(exp(-|beta z|))/beta   (torch.nn.Softplus(beta, threshold=20): for beta*z > 20
+// this differs from the reference's linear branch by < 2.1e-9/beta, far under fp32 resolution of z)
+__device__ __forceinline__ float softplus_k(float z, const EpiConst& k) {
+  const float e = ex2_approx(-fabsf(z * k.nbl2));
+  return fmaf(lg2_approx(1.f + e), k.ln2_over_beta, fmaxf(z, 0.f));
+}
+// 1 - act'(z) recovered from the stored activation a = act(z):  exp(-beta a) = 1 - sigmoid(beta z);  relu: [a <= 0]
+__device__ __forceinline__ float one_minus_dact(float a, const EpiConst& k) {
+  return k.relu ? (a > 0.f ? 0.f : 1.f) : ex2_approx(a * k.nbl2);
+}
+
+template <bool PAR>
+struct Packed32 {
+  uint4 h[4];
+  uint4 l[PAR ? 4 : 1];
+};
+template <bool PAR>
+__device__ __forceinline__ void ldg_chunk(const Epi& e, int c0, const uint8_t* img, Packed32<PAR>& pk) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pk.h[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow));
+    if (PAR) pk.l[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow + kParityPoints));
+  }
+}
+template <int DT, bool PAR>
+__device__ __forceinline__ void granule8(const Packed32<PAR>& pk, int j, float (&o)[8]) {
+  unpack8<DT>(pk.h[j], o);
+  if (PAR) unpack8_add<DT>(pk.l[j], o);
+}
+// 8 values of this thread's point -> one granule of a global image (parity: hi row and lo row)
+template <int DT, bool PAR>
+__device__ __forceinline__ void stg_granule8(const Epi& e, uint8_t* img, int c0, int j, const float (&v)[8]) {
+  if (!PAR) {
+    *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = pack8<DT>(v);
+  } else {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      hi[t] = H16<DT>::rnd(v[t]);
+      lo[t] = v[t] - hi[t];
+    }
+    *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = pack8<DT>(hi);
+    *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow + kParityPoints)) = pack8<DT>(lo);
+  }
+}
+
+// 8 values of this thread's point -> one granule of the A image in shared memory and (optionally) of a global image
+template <int DT, bool PAR>
+__device__ __forceinline__ void put_granule8(const Epi& e, uint8_t* img, int c0, int j, const float (&v)[8]) {
+  if (!PAR) {
+    const uint4 pk = pack8<DT>(v);
+    st_smem_v4(e.sA + img_off(c0, j, e.prow), pk);
+    if (img) *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = pk;
+  } else {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      hi[t] = H16<DT>::rnd(v[t]);
+      lo[t] = v[t] - hi[t];
+    }
+    const uint4 ph = pack8<DT>(hi), pl = pack8<DT>(lo);
+    st_smem_v4(e.sA + img_off(c0, j, e.prow), ph);
+    st_smem_v4(e.sA + img_off(c0, j, e.prow + kParityPoints), pl);
+    if (img) {
+      *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = ph;
+      *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow + kParityPoints)) = pl;
+    }
+  }
+}
+
+// The arithmetic of one 32-column chunk of a hidden-layer epilogue.  v: accumulator columns in, result out.
+template <int DT, bool PAR, int EPI>
+__device__ __forceinline__ void chunk_math(const Epi& e, const StepIO& io, const EpiConst& k, int c0, float (&v)[32],
+                                           const Packed32<PAR>& xa, const Packed32<PAR>& xb, float* gskip) {
+  const bool last = io.special && (c0 + 32 == k.H);
+  if (EPI == EPI_FWD_HIDDEN) {
+    // a_l = act(z_l + b_l)                                          reference model/networks.py:100-102
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(io.vec + c0 + 8 * j));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(io.vec + c0 + 8 * j + 4));
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float z = v[8 * j + t] + b[t];
+        v[8 * j + t] = k.relu ? fmaxf(z, 0.f) : softplus_k(z, k);
+      }
+    }
+    if (last) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }  // skip-in: next layer sees [a ; x] (networks.py:94-95)
+  } else if (EPI == EPI_REV_HIDDEN) {
+    // q_{l-1} = (q_l W_l) * act'(z_{l-1})                            autograd of networks.py:100-102 (losses.py:289-295)
+    if (last) {
+      // rows H-3..H-1 of W_skip multiply the raw input: their product is d f / d x through the skip
+      gskip[e.prow * 3 + 0] = v[29]; gskip[e.prow * 3 + 1] = v[30]; gskip[e.prow * 3 + 2] = v[31];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a[8];
+      granule8<DT, PAR>(xa, j, a);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[8 * j + t] *= 1.f - one_minus_dact(a[t], k);
+    }
+    if (last) v[29] = v[30] = v[31] = 0.f;
+  } else if (EPI == EPI_TAN_HIDDEN) {
+    // zdot_l in v;  adot_l = s' zdot_l -> next A;  u_l = act''(z_l) s_l zdot_l = beta (1 - s') q_l zdot_l
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a[8];
+      granule8<DT, PAR>(xa, j, a);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) a[t] = one_minus_dact(a[t], k);
+      if (last && j == 3) a[5] = a[6] = a[7] = 1.f;  // input columns: no activation state
+      if (!k.relu) {
+        float q[8];
+        granule8<DT, PAR>(xb, j, q);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) q[t] = k.beta * a[t] * q[t] * v[8 * j + t];
+        stg_granule8<DT, PAR>(e, io.out_u, c0, j, q);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[8 * j + t] *= 1.f - a[t];
+    }
+    if (last) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }  // tangent of the injected input = g-bar
+  } else if (EPI == EPI_ADJ_HIDDEN) {
+    // Zbar_l = s' (Zbar_{l+1} W_{l+1}) + u_l
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a[8];
+      granule8<DT, PAR>(xa, j, a);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) a[t] = 1.f - one_minus_dact(a[t], k);
+      if (last && j == 3) a[5] = a[6] = a[7] = 0.f;  // those rows fed the raw input
+      if (io.in_b) {
+        float u[8];
+        granule8<DT, PAR>(xb, j, u);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[8 * j + t] = fmaf(a[t], v[8 * j + t], u[t]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[8 * j + t] *= a[t];
+      }
+    }
+  }
+}
+
+// Hidden-layer epilogue, general form: wait for the whole accumulator, then walk the columns.  Used in parity mode
+// and whenever the GEMM has a single column group (H <= 256).
+template <int DT, bool PAR, int EPI>
+__device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
+                                                  uint32_t par0, uint32_t par1, float* gskip) {
+  mbar_wait(&B.acc_full[0], par0);
+  if (st.n_groups == 2) mbar_wait(&B.acc_full[1], par1);
+  tc_fence_after();
+  const int nIt = k.H / 64;
+  for (int it = 0; it < nIt; ++it) {
+    const int c0 = it * 64 + e.h * 32;
+    float v[32];
+    load_acc32<PAR>(e, c0, v);
+    if (e.math) {
+      Packed32<PAR> xa, xb;
+      if (EPI != EPI_FWD_HIDDEN) ldg_chunk<PAR>(e, c0, io.in_a, xa);
+      if (io.in_b) ldg_chunk<PAR>(e, c0, io.in_b, xb);
+      chunk_math<DT, PAR, EPI>(e, io, k, c0, v, xa, xb, gskip);
+      store_chunk<DT, PAR>(e, c0, v, io.out, true);
+    }
+  }
+  fence_proxy_async_smem();
+  if (st.signal) {
+    tc_fence_before();
+    mbar_arrive(B.a_lo);
+    mbar_arrive(B.a_hi);
+  }
+}
+
+// Hidden-layer epilogue, overlapped form (fast mode, H = 512: two accumulator halves of 256 columns).
+//   half 0 is processed while the MMAs of half 1 still read the A image, so its packed 16-bit result cannot go
+//   to shared memory yet: it is parked in TMEM, in the first 16 of the 32 accumulator columns the thread has just
+//   consumed.  Once half 1 is complete the parked columns move into the A image (-> a_lo: the next GEMM may start
+//   on K < 256 and overwrite accumulator half 0) and half 1 is processed straight into the A image (-> a_hi).
+// Spill-image operands of chunk i+1 are requested before the arithmetic of chunk i.
+template <int DT, int EPI>
+__device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
+                                                   uint32_t par0, uint32_t par1, float* gskip) {
+  Packed32<false> xa, xb;
+  constexpr bool kNeedA = EPI != EPI_FWD_HIDDEN;
+  const bool need_b = io.in_b != nullptr;
+  if (kNeedA) ldg_chunk<false>(e, e.h * 32, io.in_a, xa);
+  if (need_b) ldg_chunk<false>(e, e.h * 32, io.in_b, xb);
+  mbar_wait(&B.acc_full[0], par0);
+  tc_fence_after();
+  for (int half = 0; half < 2; ++half) {
+    if (half == 1) {
+      tmem_st_wait();
+      mbar_wait(&B.acc_full[1], par1);
+      tc_fence_after();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int c0 = it * 64 + e.h * 32;
+        uint32_t r[16];
+        tmem_ld16(e.taddr + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_smem_v4(e.sA + img_off(c0, j, e.prow), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+      }
+      fence_proxy_async_smem();
+      if (st.signal) {
+        tc_fence_before();
+        mbar_arrive(B.a_lo);
+      }
+    }
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const int c0 = half * 256 + it * 64 + e.h * 32;
+      uint32_t r[32];
+      tmem_ld32(e.taddr + c0, r);
+      Packed32<false> na, nb;
+      if (half == 0 || it < 3) {
+        if (kNeedA) ldg_chunk<false>(e, c0 + 64, io.in_a, na);
+        if (need_b) ldg_chunk<false>(e, c0 + 64, io.in_b, nb);
+      }
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      chunk_math<DT, false, EPI>(e, io, k, c0, v, xa, xb, gskip);
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = H16<DT>::pack(v[2 * j], v[2 * j + 1]);
+      if (io.out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(io.out + img_off(c0, j, e.prow)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+      if (half == 0) {
+        tmem_st16(e.taddr + c0, pk);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_smem_v4(e.sA + img_off(c0, j, e.prow), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+      }
+      if (kNeedA) xa = na;
+      if (need_b) xb = nb;
+    }
+  }
+  fence_proxy_async_smem();
+  if (st.signal) {
+    tc_fence_before();
+    mbar_arrive(B.a_hi);
+  }
+}
+
+template <int DT, bool PAR, int EPI>
+__device__ __forceinline__ void hidden_step(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
+                                            uint32_t& n0, uint32_t& n1, float* gskip) {
+  if (!PAR && st.n_groups == 2) hidden_step_staged<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+  else hidden_step_plain<DT, PAR, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+  ++n0;
+  if (st.n_groups == 2) ++n1;
+}
+
 template <int DT, bool PAR>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
   using Cfg = ChainCfg<PAR>;
@@ -266,9 +550,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
   uint64_t* w_full = bars;            // [NST]
   uint64_t* w_empty = bars + NST;     // [NST]
-  uint64_t* acc_full = bars + 2 * NST;
-  uint64_t* a_ready = bars + 2 * NST + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2);
+  Bars B;
+  B.acc_full = bars + 2 * NST;        // [2]
+  B.a_lo = bars + 2 * NST + 2;
+  B.a_hi = bars + 2 * NST + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
   float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
@@ -279,8 +565,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(a_ready, kEpiThreads);
+    mbar_init(&B.acc_full[0], 1);
+    mbar_init(&B.acc_full[1], 1);
+    mbar_init(B.a_lo, kEpiThreads);
+    mbar_init(B.a_hi, kEpiThreads);
     mbar_fence_init();
   }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
@@ -289,8 +577,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t ib = img_bytes(p.H);
-  const bool relu = (p.flags & FL_RELU) != 0;
 
+  // register file re-split (per SM sub-partition: 16384 registers = 1 light warp + 2 epilogue warps)
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
@@ -313,18 +603,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      uint32_t stage = 0, round = 0, gemm = 0;
+      uint32_t stage = 0, round = 0, n0 = 0;
       const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int s = 0; s < p.n_steps; ++s) {
           const StepDesc& st = p.steps[s];
           if (st.n_groups == 0) continue;
-          mbar_wait(a_ready, gemm & 1);
-          tc_fence_after();
+          const uint32_t par = n0 & 1;
           const uint32_t idesc = make_idesc_f16(kTileRows, st.ng, DT == DT_BF16, false, false);
           const uint32_t b_lbo = static_cast<uint32_t>(st.ng) * 16;
           for (int g = 0; g < st.n_groups; ++g) {
             for (int kc = 0; kc < st.kchunks; ++kc) {
+              if (g == 0) {
+                // the A image becomes available in two parts (hidden_step_staged)
+                if (kc == 0) {
+                  mbar_wait(B.a_lo, par);
+                  if (st.k_lo == 0) mbar_wait(B.a_hi, par);
+                  tc_fence_after();
+                } else if (kc == st.k_lo) {
+                  mbar_wait(B.a_hi, par);
+                  tc_fence_after();
+                }
+              }
               mbar_wait(&w_full[stage], round & 1);
               tc_fence_after();
               const uint32_t a_addr = sA_u + static_cast<uint32_t>((kc % st.a_chunks) * st.k16 * 2) * kGranuleBytes;
@@ -337,14 +637,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               umma_commit(&w_empty[stage]);
               if (++stage == NST) { stage = 0; ++round; }
             }
+            umma_commit(&B.acc_full[g]);
           }
-          umma_commit(acc_full);
-          ++gemm;
+          ++n0;
         }
       }
     }
+  }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     Epi e;
     e.sA = smem_u32(sA);
     const int q = warp & 3;
@@ -355,13 +657,21 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     e.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     e.fval = 0.f;
     e.fb = 0.f;
-    uint32_t gemm = 0;
+    uint32_t n0 = 0, n1 = 0;  // GEMM steps seen / GEMM steps with two column groups seen (barrier phases)
+    EpiConst k;
+    k.H = p.H;
+    k.beta = p.beta;
+    k.inv_beta = p.inv_beta;
+    k.nbl2 = -p.beta * 1.4426950408889634f;
+    k.ln2_over_beta = 0.6931471805599453f * p.inv_beta;
+    k.relu = (p.flags & FL_RELU) != 0;
+    const bool relu = k.relu;
     const int nIt = p.H / 64;
-    const float beta = p.beta, inv_beta = p.inv_beta;
     const float mult = p.seed_mult ? __ldg(p.seed_mult) : 1.f;
     // layer whose image carries the raw input in its last three columns (feeds the skip layer): those columns have no
-    // activation state, their derivative factor must read as 0 (and exp(-beta x) may overflow for x < 0)
+    // activation state, their derivative factor must read as 0
     const int inj_layer = p.skip > 0 ? p.skip - 1 : -1;
+    const bool has_u = (p.flags & FL_TANGENT) && !relu;
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       e.tile = tile;
@@ -429,37 +739,31 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         }
       }
       fence_proxy_async_smem();
+      if (p.steps[0].n_groups != 0) {
+        tc_fence_before();
+        mbar_arrive(B.a_lo);
+        mbar_arrive(B.a_hi);
+      }
 
       for (int s = 0; s < p.n_steps; ++s) {
         const StepDesc& st = p.steps[s];
-        if (st.n_groups != 0) {
-          tc_fence_before();
-          mbar_arrive(a_ready);
-          mbar_wait(acc_full, gemm & 1);
-          tc_fence_after();
-          ++gemm;
-        }
         const int l = st.layer;
+        StepIO io;
+        io.in_a = io.in_b = nullptr;
+        io.out = io.out_u = nullptr;
+        io.vec = nullptr;
+        io.special = false;
         switch (st.epi) {
           case EPI_FWD_HIDDEN: {
-            uint8_t* aimg = (p.flags & FL_SPILL_A) ? img_ptr(p.Aimg, l, p.n_tiles, tile, ib) : nullptr;
-            const bool inject = l == inj_layer;
-            for (int it = 0; it < nIt; ++it) {
-              const int c0 = it * 64 + e.h * 32;
-              float v[32];
-              load_acc32<PAR>(e, c0, v);
-              if (e.math) {
-                float b[32];
-                load_vec32(p.bias + l * p.H + c0, b);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j] + b[j], beta, inv_beta, relu);
-                if (inject && c0 + 32 == p.H) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }
-                store_chunk<DT, PAR>(e, c0, v, aimg, true);
-              }
-            }
-            fence_proxy_async_smem();
+            io.out = (p.flags & FL_SPILL_A) ? img_ptr(p.Aimg, l, p.n_tiles, tile, ib) : nullptr;
+            io.vec = p.bias + l * p.H;
+            io.special = l == inj_layer;
+            hidden_step<DT, PAR, EPI_FWD_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           case EPI_FWD_LAST: {
+            mbar_wait(&B.acc_full[0], n0 & 1);
+            tc_fence_after();
+            ++n0;
             if (e.h == 0) {
               float v[32];
               load_acc32<PAR>(e, 0, v);
@@ -477,41 +781,38 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             if (e.math) {
               for (int it = 0; it < nIt; ++it) {
                 const int c0 = it * 64 + e.h * 32;
-                float a[32], w[32];
-                load_vec32(p.w_last + c0, w);
-                load_chunk_smem<DT, PAR>(e, c0, a);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = w[j] * (1.f - act_em(a[j], beta, relu));
-                store_chunk<DT, PAR>(e, c0, a, qimg, true);
+                for (int j = 0; j < 4; ++j) {
+                  float a[8];
+                  unpack8<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow)), a);
+                  if (PAR) unpack8_add<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow + kParityPoints)), a);
+                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j));
+                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j + 4));
+                  const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) a[t] = w[t] * (1.f - one_minus_dact(a[t], k));
+                  put_granule8<DT, PAR>(e, qimg, c0, j, a);
+                }
               }
             }
             fence_proxy_async_smem();
+            if (st.signal) {
+              tc_fence_before();
+              mbar_arrive(B.a_lo);
+              mbar_arrive(B.a_hi);
+            }
           } break;
           case EPI_REV_HIDDEN: {
             // GEMM r = q_l W_l done; q_{l-1} = r * act'(z_{l-1});  l = st.layer
-            const uint8_t* aimg = img_ptr(p.Aimg, l - 1, p.n_tiles, tile, ib);
-            uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l - 1, p.n_tiles, tile, ib) : nullptr;
-            const bool is_skip = (l - 1) == inj_layer;
-            for (int it = 0; it < nIt; ++it) {
-              const int c0 = it * 64 + e.h * 32;
-              float v[32];
-              load_acc32<PAR>(e, c0, v);
-              if (e.math) {
-                float a[32];
-                load_chunk_global<DT, PAR>(e, c0, aimg, a);
-                if (is_skip && c0 + 32 == p.H) {
-                  // rows H-3..H-1 of W_skip multiply the raw input: their product is d f / d x through the skip
-                  gskip[e.prow * 3 + 0] = v[29]; gskip[e.prow * 3 + 1] = v[30]; gskip[e.prow * 3 + 2] = v[31];
-                  a[29] = a[30] = a[31] = 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = v[j] * (1.f - act_em(a[j], beta, relu));
-                store_chunk<DT, PAR>(e, c0, v, qimg, true);
-              }
-            }
-            fence_proxy_async_smem();
+            io.in_a = img_ptr(p.Aimg, l - 1, p.n_tiles, tile, ib);
+            io.out = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l - 1, p.n_tiles, tile, ib) : nullptr;
+            io.special = (l - 1) == inj_layer;
+            hidden_step<DT, PAR, EPI_REV_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           case EPI_REV_LAST: {
+            mbar_wait(&B.acc_full[0], n0 & 1);
+            tc_fence_after();
+            ++n0;
             named_bar_sync(1, kEpiThreads);  // gskip written by the h=1 warps of an earlier step
             if (e.h == 0) {
               float v[32];
@@ -533,89 +834,56 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             named_bar_sync(1, kEpiThreads);  // gskip may be rewritten by the next tile
           } break;
           case EPI_TAN_HIDDEN: {
-            // zdot_l in TMEM;  adot_l = s' zdot_l -> next A;  u_l = beta (1-s') q_l zdot_l
-            const uint8_t* aimg = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
-            const uint8_t* qimg = img_ptr(p.Qimg, l, p.n_tiles, tile, ib);
-            uint8_t* adimg = img_ptr(p.ADimg, l, p.n_tiles, tile, ib);
-            uint8_t* uimg = relu ? nullptr : img_ptr(p.Uimg, l, p.n_tiles, tile, ib);
-            const bool inject = l == inj_layer;
-            for (int it = 0; it < nIt; ++it) {
-              const int c0 = it * 64 + e.h * 32;
-              float zd[32];
-              load_acc32<PAR>(e, c0, zd);
-              if (e.math) {
-                float a[32];
-                load_chunk_global<DT, PAR>(e, c0, aimg, a);
-                if (inject && c0 + 32 == p.H) a[29] = a[30] = a[31] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = act_em(a[j], beta, relu);  // a := 1 - s'
-                if (!relu) {
-                  float qv[32];
-                  load_chunk_global<DT, PAR>(e, c0, qimg, qv);
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) qv[j] = beta * a[j] * qv[j] * zd[j];
-                  store_chunk<DT, PAR>(e, c0, qv, uimg, false);
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) zd[j] = (1.f - a[j]) * zd[j];
-                if (inject && c0 + 32 == p.H) { zd[29] = e.x[0]; zd[30] = e.x[1]; zd[31] = e.x[2]; }
-                store_chunk<DT, PAR>(e, c0, zd, adimg, true);
-              }
-            }
-            fence_proxy_async_smem();
+            io.in_a = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
+            io.in_b = relu ? nullptr : img_ptr(p.Qimg, l, p.n_tiles, tile, ib);
+            io.out = img_ptr(p.ADimg, l, p.n_tiles, tile, ib);
+            io.out_u = relu ? nullptr : img_ptr(p.Uimg, l, p.n_tiles, tile, ib);
+            io.special = l == inj_layer;
+            hidden_step<DT, PAR, EPI_TAN_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           case EPI_ADJ_START: {
             // Zbar_{L-1} = s' * (w_L fbar) + u_{L-1}
             const uint8_t* aimg = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
-            const bool has_u = (p.flags & FL_TANGENT) && !relu;
             const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
             uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
             if (e.math) {
               for (int it = 0; it < nIt; ++it) {
                 const int c0 = it * 64 + e.h * 32;
-                float a[32], w[32];
-                load_vec32(p.w_last + c0, w);
-                load_chunk_global<DT, PAR>(e, c0, aimg, a);
+                Packed32<PAR> xa, xu;
+                ldg_chunk<PAR>(e, c0, aimg, xa);
+                if (has_u) ldg_chunk<PAR>(e, c0, uimg, xu);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = (1.f - act_em(a[j], beta, relu)) * (w[j] * e.fb);
-                if (has_u) {
-                  float u[32];
-                  load_chunk_global<DT, PAR>(e, c0, uimg, u);
+                for (int j = 0; j < 4; ++j) {
+                  float a[8];
+                  granule8<DT, PAR>(xa, j, a);
+                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j));
+                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j + 4));
+                  const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) a[j] += u[j];
+                  for (int t = 0; t < 8; ++t) a[t] = (1.f - one_minus_dact(a[t], k)) * (w[t] * e.fb);
+                  if (has_u) {
+                    float u[8];
+                    granule8<DT, PAR>(xu, j, u);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) a[t] += u[t];
+                  }
+                  put_granule8<DT, PAR>(e, zimg, c0, j, a);
                 }
-                store_chunk<DT, PAR>(e, c0, a, zimg, true);
               }
             }
             fence_proxy_async_smem();
+            if (st.signal) {
+              tc_fence_before();
+              mbar_arrive(B.a_lo);
+              mbar_arrive(B.a_hi);
+            }
           } break;
           case EPI_ADJ_HIDDEN: {
-            // GEMM abar = Zbar_{l+1} W_{l+1} done;  Zbar_l = s' abar + u_l
-            const uint8_t* aimg = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
-            const bool has_u = (p.flags & FL_TANGENT) && !relu;
-            const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
-            uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
-            const bool from_skip = l == inj_layer;
-            for (int it = 0; it < nIt; ++it) {
-              const int c0 = it * 64 + e.h * 32;
-              float v[32];
-              load_acc32<PAR>(e, c0, v);
-              if (e.math) {
-                float a[32];
-                load_chunk_global<DT, PAR>(e, c0, aimg, a);
-                if (from_skip && c0 + 32 == p.H) a[29] = a[30] = a[31] = 0.f;  // those rows fed the raw input
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (1.f - act_em(a[j], beta, relu)) * v[j];
-                if (has_u) {
-                  float u[32];
-                  load_chunk_global<DT, PAR>(e, c0, uimg, u);
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] += u[j];
-                }
-                store_chunk<DT, PAR>(e, c0, v, zimg, true);
-              }
-            }
-            fence_proxy_async_smem();
+            io.in_a = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
+            io.in_b = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
+            io.out = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
+            io.special = l == inj_layer;
+            hidden_step<DT, PAR, EPI_ADJ_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           default: break;
         }
