@@ -348,77 +348,81 @@ __device__ __forceinline__ void put_granule8(const Epi& e, uint8_t* img, int c0,
   }
 }
 
-// The arithmetic of one 32-column chunk of a hidden-layer epilogue.  v: accumulator columns in, result out.
+// Operands of one 32-column chunk that come from memory: forward = the bias row (fp32, 8 floats per granule split
+// over xa.h[j] / xb.h[j]); other sweeps = the activation image (xa) and the q / u image (xb).
 template <int DT, bool PAR, int EPI>
-__device__ __forceinline__ void chunk_math(const Epi& e, const StepIO& io, const EpiConst& k, int c0, float (&v)[32],
-                                           const Packed32<PAR>& xa, const Packed32<PAR>& xb, float* gskip) {
-  const bool last = io.special && (c0 + 32 == k.H);
+__device__ __forceinline__ void load_aux(const Epi& e, const StepIO& io, int c0, Packed32<PAR>& xa, Packed32<PAR>& xb) {
   if (EPI == EPI_FWD_HIDDEN) {
-    // a_l = act(z_l + b_l)                                          reference model/networks.py:100-102
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(io.vec + c0 + 8 * j));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(io.vec + c0 + 8 * j + 4));
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float z = v[8 * j + t] + b[t];
-        v[8 * j + t] = k.relu ? fmaxf(z, 0.f) : softplus_k(z, k);
-      }
+      xa.h[j] = __ldg(reinterpret_cast<const uint4*>(io.vec + c0 + 8 * j));
+      xb.h[j] = __ldg(reinterpret_cast<const uint4*>(io.vec + c0 + 8 * j + 4));
     }
-    if (last) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }  // skip-in: next layer sees [a ; x] (networks.py:94-95)
+  } else {
+    ldg_chunk<PAR>(e, c0, io.in_a, xa);
+    if (io.in_b) ldg_chunk<PAR>(e, c0, io.in_b, xb);
+  }
+}
+
+// The arithmetic of one granule (8 columns starting at column c) of a hidden-layer epilogue.
+// v: accumulator columns in, result out.  j: granule index inside the 32-column chunk the operands were loaded for.
+template <int DT, bool PAR, int EPI>
+__device__ __forceinline__ void granule_math(const Epi& e, const StepIO& io, const EpiConst& k, int c, int j, float (&v)[8],
+                                             const Packed32<PAR>& xa, const Packed32<PAR>& xb, float* gskip) {
+  const bool last = io.special && (c + 8 == k.H);  // columns H-3..H-1 carry the raw input (skip-in)
+  if (EPI == EPI_FWD_HIDDEN) {
+    // a_l = act(z_l + b_l)                                          reference model/networks.py:100-102
+    const float b[8] = {__uint_as_float(xa.h[j].x), __uint_as_float(xa.h[j].y), __uint_as_float(xa.h[j].z), __uint_as_float(xa.h[j].w),
+                        __uint_as_float(xb.h[j].x), __uint_as_float(xb.h[j].y), __uint_as_float(xb.h[j].z), __uint_as_float(xb.h[j].w)};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float z = v[t] + b[t];
+      v[t] = k.relu ? fmaxf(z, 0.f) : softplus_k(z, k);
+    }
+    if (last) { v[5] = e.x[0]; v[6] = e.x[1]; v[7] = e.x[2]; }  // next layer sees [a ; x] (networks.py:94-95)
   } else if (EPI == EPI_REV_HIDDEN) {
     // q_{l-1} = (q_l W_l) * act'(z_{l-1})                            autograd of networks.py:100-102 (losses.py:289-295)
     if (last) {
       // rows H-3..H-1 of W_skip multiply the raw input: their product is d f / d x through the skip
-      gskip[e.prow * 3 + 0] = v[29]; gskip[e.prow * 3 + 1] = v[30]; gskip[e.prow * 3 + 2] = v[31];
+      gskip[e.prow * 3 + 0] = v[5]; gskip[e.prow * 3 + 1] = v[6]; gskip[e.prow * 3 + 2] = v[7];
     }
+    float a[8];
+    granule8<DT, PAR>(xa, j, a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a[8];
-      granule8<DT, PAR>(xa, j, a);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[8 * j + t] *= 1.f - one_minus_dact(a[t], k);
-    }
-    if (last) v[29] = v[30] = v[31] = 0.f;
+    for (int t = 0; t < 8; ++t) v[t] *= 1.f - one_minus_dact(a[t], k);
+    if (last) v[5] = v[6] = v[7] = 0.f;
   } else if (EPI == EPI_TAN_HIDDEN) {
     // zdot_l in v;  adot_l = s' zdot_l -> next A;  u_l = act''(z_l) s_l zdot_l = beta (1 - s') q_l zdot_l
+    float a[8];
+    granule8<DT, PAR>(xa, j, a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a[8];
-      granule8<DT, PAR>(xa, j, a);
+    for (int t = 0; t < 8; ++t) a[t] = one_minus_dact(a[t], k);
+    if (last) a[5] = a[6] = a[7] = 1.f;  // input columns: no activation state
+    if (!k.relu) {
+      float q[8];
+      granule8<DT, PAR>(xb, j, q);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) a[t] = one_minus_dact(a[t], k);
-      if (last && j == 3) a[5] = a[6] = a[7] = 1.f;  // input columns: no activation state
-      if (!k.relu) {
-        float q[8];
-        granule8<DT, PAR>(xb, j, q);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) q[t] = k.beta * a[t] * q[t] * v[8 * j + t];
-        stg_granule8<DT, PAR>(e, io.out_u, c0, j, q);
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[8 * j + t] *= 1.f - a[t];
+      for (int t = 0; t < 8; ++t) q[t] = k.beta * a[t] * q[t] * v[t];
+      stg_granule8<DT, PAR>(e, io.out_u, c, 0, q);
     }
-    if (last) { v[29] = e.x[0]; v[30] = e.x[1]; v[31] = e.x[2]; }  // tangent of the injected input = g-bar
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] *= 1.f - a[t];
+    if (last) { v[5] = e.x[0]; v[6] = e.x[1]; v[7] = e.x[2]; }  // tangent of the injected input = g-bar
   } else if (EPI == EPI_ADJ_HIDDEN) {
     // Zbar_l = s' (Zbar_{l+1} W_{l+1}) + u_l
+    float a[8];
+    granule8<DT, PAR>(xa, j, a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a[8];
-      granule8<DT, PAR>(xa, j, a);
+    for (int t = 0; t < 8; ++t) a[t] = 1.f - one_minus_dact(a[t], k);
+    if (last) a[5] = a[6] = a[7] = 0.f;  // those rows fed the raw input
+    if (io.in_b) {
+      float u[8];
+      granule8<DT, PAR>(xb, j, u);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) a[t] = 1.f - one_minus_dact(a[t], k);
-      if (last && j == 3) a[5] = a[6] = a[7] = 0.f;  // those rows fed the raw input
-      if (io.in_b) {
-        float u[8];
-        granule8<DT, PAR>(xb, j, u);
+      for (int t = 0; t < 8; ++t) v[t] = fmaf(a[t], v[t], u[t]);
+    } else {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[8 * j + t] = fmaf(a[t], v[8 * j + t], u[t]);
-      } else {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[8 * j + t] *= a[t];
-      }
+      for (int t = 0; t < 8; ++t) v[t] *= a[t];
     }
   }
 }
@@ -438,10 +442,15 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
     load_acc32<PAR>(e, c0, v);
     if (e.math) {
       Packed32<PAR> xa, xb;
-      if (EPI != EPI_FWD_HIDDEN) ldg_chunk<PAR>(e, c0, io.in_a, xa);
-      if (io.in_b) ldg_chunk<PAR>(e, c0, io.in_b, xb);
-      chunk_math<DT, PAR, EPI>(e, io, k, c0, v, xa, xb, gskip);
-      store_chunk<DT, PAR>(e, c0, v, io.out, true);
+      load_aux<DT, PAR, EPI>(e, io, c0, xa, xb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float w[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[t] = v[8 * j + t];
+        granule_math<DT, PAR, EPI>(e, io, k, c0 + 8 * j, j, w, xa, xb, gskip);
+        put_granule8<DT, PAR>(e, io.out, c0, j, w);
+      }
     }
   }
   fence_proxy_async_smem();
@@ -457,31 +466,52 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
 //   to shared memory yet: it is parked in TMEM, in the first 16 of the 32 accumulator columns the thread has just
 //   consumed.  Once half 1 is complete the parked columns move into the A image (-> a_lo: the next GEMM may start
 //   on K < 256 and overwrite accumulator half 0) and half 1 is processed straight into the A image (-> a_hi).
-// Spill-image operands of chunk i+1 are requested before the arithmetic of chunk i.
+// Latency hiding inside the two epilogue warps of each SM sub-partition: every spill-image line the step will read
+// is first requested into L2 (prefetch.global.L2, while the MMAs of the step are still running), the memory
+// operands travel through an NBUF-slot register ring filled NBUF chunks ahead of their use, and the TMEM reads are
+// double-buffered in 16-column pieces.
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 template <int DT, int EPI>
 __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
-  Packed32<false> xa, xb;
-  constexpr bool kNeedA = EPI != EPI_FWD_HIDDEN;
-  const bool need_b = io.in_b != nullptr;
-  if (kNeedA) ldg_chunk<false>(e, e.h * 32, io.in_a, xa);
-  if (need_b) ldg_chunk<false>(e, e.h * 32, io.in_b, xb);
+  // ring depth: forward (bias row, 32 registers per chunk) and reverse (one image, 16) cover a whole half; tangent
+  // and adjoint (two images, 32 per chunk, plus more live arithmetic) keep two chunks in flight
+  constexpr int NBUF = (EPI == EPI_REV_HIDDEN) ? 4 : 2;
+  if (EPI != EPI_FWD_HIDDEN) {
+#pragma unroll 1
+    for (int ci = 0; ci < 8; ++ci) {
+      const int c0 = ci * 64 + e.h * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        prefetch_l2(io.in_a + img_off(c0, j, e.prow));
+        if (io.in_b) prefetch_l2(io.in_b + img_off(c0, j, e.prow));
+      }
+    }
+  }
+  Packed32<false> xa[NBUF], xb[NBUF];
+#pragma unroll
+  for (int it = 0; it < NBUF; ++it) load_aux<DT, false, EPI>(e, io, it * 64 + e.h * 32, xa[it], xb[it]);
   mbar_wait(&B.acc_full[0], par0);
   tc_fence_after();
+#pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     if (half == 1) {
       tmem_st_wait();
       mbar_wait(&B.acc_full[1], par1);
       tc_fence_after();
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int c0 = it * 64 + e.h * 32;
-        uint32_t r[16];
-        tmem_ld16(e.taddr + c0, r);
+      for (int pair = 0; pair < 2; ++pair) {
+        uint32_t r0[16], r1[16];
+        const int c0 = pair * 128 + e.h * 32;
+        tmem_ld16(e.taddr + c0, r0);
+        tmem_ld16(e.taddr + c0 + 64, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_smem_v4(e.sA + img_off(c0, j, e.prow), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+        for (int j = 0; j < 4; ++j) {
+          st_smem_v4(e.sA + img_off(c0, j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
+          st_smem_v4(e.sA + img_off(c0 + 64, j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
+        }
       }
       fence_proxy_async_smem();
       if (st.signal) {
@@ -489,38 +519,44 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
         mbar_arrive(B.a_lo);
       }
     }
-#pragma unroll 1
+    const int cbase = half * 256 + e.h * 32;
+    uint32_t r[2][16];
+    tmem_ld16(e.taddr + cbase, r[0]);
+#pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int c0 = half * 256 + it * 64 + e.h * 32;
-      uint32_t r[32];
-      tmem_ld32(e.taddr + c0, r);
-      Packed32<false> na, nb;
-      if (half == 0 || it < 3) {
-        if (kNeedA) ldg_chunk<false>(e, c0 + 64, io.in_a, na);
-        if (need_b) ldg_chunk<false>(e, c0 + 64, io.in_b, nb);
+      constexpr int kDummy = 0;
+      (void)kDummy;
+      const int slot = it % NBUF;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c = cbase + it * 64 + sub * 16;  // first column of this 16-column piece
+        tmem_ld_wait();
+        if (!(it == 3 && sub == 1)) tmem_ld16(e.taddr + (sub == 0 ? c + 16 : c + 48), r[sub ^ 1]);
+        uint32_t pk[8];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          float w[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r[sub][8 * jj + t]);
+          granule_math<DT, false, EPI>(e, io, k, c + 8 * jj, 2 * sub + jj, w, xa[slot], xb[slot], gskip);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) pk[4 * jj + t] = H16<DT>::pack(w[2 * t], w[2 * t + 1]);
+        }
+        const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (io.out) {
+          *reinterpret_cast<uint4*>(io.out + img_off(c, 0, e.prow)) = p0;
+          *reinterpret_cast<uint4*>(io.out + img_off(c, 1, e.prow)) = p1;
+        }
+        if (half == 0) {
+          tmem_st8(e.taddr + cbase + it * 64 + sub * 8, pk);
+        } else {
+          st_smem_v4(e.sA + img_off(c, 0, e.prow), p0);
+          st_smem_v4(e.sA + img_off(c, 1, e.prow), p1);
+        }
       }
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      chunk_math<DT, false, EPI>(e, io, k, c0, v, xa, xb, gskip);
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = H16<DT>::pack(v[2 * j], v[2 * j + 1]);
-      if (io.out) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(io.out + img_off(c0, j, e.prow)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-      }
-      if (half == 0) {
-        tmem_st16(e.taddr + c0, pk);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_smem_v4(e.sA + img_off(c0, j, e.prow), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
-      }
-      if (kNeedA) xa = na;
-      if (need_b) xb = nb;
+      // refill this slot with the chunk NBUF positions ahead (chunk index = half * 4 + it)
+      if (half * 4 + it + NBUF < 8)
+        load_aux<DT, false, EPI>(e, io, (half * 4 + it + NBUF) * 64 + e.h * 32, xa[slot], xb[slot]);
     }
   }
   fence_proxy_async_smem();
