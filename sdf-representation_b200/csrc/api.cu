@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include "../../include/sdfnet.h"
@@ -304,6 +305,8 @@ static void base_params(const sdfnet_handle* h, ChainParams& p) {
   p.inv_beta = h->relu ? 0.f : 1.f / h->d.beta;
   p.bias = h->bias; p.w_last = h->w_last; p.wpack = h->wpack;
   p.flags = h->relu ? FL_RELU : 0u;
+  static const uint32_t dbg = [] { const char* e = getenv("SDFNET_DEBUG_FLAGS"); return e ? static_cast<uint32_t>(strtoul(e, nullptr, 0)) : 0u; }();
+  p.flags |= dbg & 0xffff0000u;
 }
 static void prog_forward(const sdfnet_handle* h, ChainParams& p) {
   for (int l = 0; l < h->L; ++l) add_step(p, EPI_FWD_HIDDEN, l, &h->F[l]);

@@ -17,21 +17,33 @@
 //            stream carries W_hi chunks then W_lo chunks.  One M=128 accumulator then holds v_hi.(W_hi+W_lo) in lanes
 //            0-63 and v_lo.(W_hi+W_lo) in lanes 64-127; the epilogue adds the two lane halves (fp32-grade result).
 //
-// Warp roles (384 threads = 3 warpgroups; setmaxnreg moves registers from the third warpgroup to the epilogue warps):
-// warps 0-7 epilogue (warp e owns TMEM lanes 32*(e%4).., columns half e/4 of each
-// 64-column block), warp 8 weight producer (cp.async.bulk into a ring), warp 9 MMA issuer, warps 10-11 idle.
+// Overlap (fast mode, H = 512): the 128 x 512 accumulator is two 256-column halves with their own completion
+// barriers.  The epilogue of half 0 runs while the MMAs of half 1 still read the A image; the epilogue of half 1 runs
+// while the next layer's MMAs already consume the K < 256 part of the new A image (hidden_step_staged).
+//
+// Warp roles (640 threads = 5 warpgroups; setmaxnreg moves registers from the last warpgroup to the epilogue):
+//   warps 0-15  epilogue: warp w owns TMEM lanes 32*(w%4).. (tile rows) and column quarter w/4 of every 128-column block
+//   warp 16     weight producer (cp.async.bulk into a 3-stage ring)
+//   warp 17     MMA issuer (one elected thread)
+//   warps 18-19 idle
+// Four epilogue warps per SM sub-partition give the latency hiding (TMEM reads, spill-image loads, MUFU) that the
+// accumulator hand-off needs; the arithmetic itself is MUFU-bound in the forward sweep (ex2 + lg2 per element).
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstdlib>
 #include "ptx.cuh"
 #include "sdf_internal.h"
 
 namespace sdf {
 
-constexpr int kEpiThreads = 256;
-constexpr int kChainThreads = 384;  // 3 warpgroups: 2 x epilogue, 1 x {producer, MMA issuer, 2 idle warps}
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr int kChainThreads = kEpiThreads + 128;
 constexpr uint32_t kABytes = kMaxH / 8 * kGranuleBytes;  // 131072
-constexpr uint32_t kScratchBytes = 2 * 32 * kParityPoints * 4;  // parity: lane-half exchange, [h][32 cols][64 points] fp32
+constexpr uint32_t kScratchBytes = 4 * 32 * kParityPoints * 4;  // parity: lane-half exchange, [h][32 cols][64 points] fp32
 
 template <bool PAR>
 struct ChainCfg {
@@ -115,75 +127,22 @@ struct Epi {
   uint32_t sA;      // shared address of the A image
   uint32_t taddr;   // TMEM base + this warp's lane quarter
   int prow;         // point row inside the tile (image row of the hi / only copy)
-  int h;            // column half within each 64-column block
+  int h;            // column quarter within each 128-column block (this thread's chunks start at h*32 + 128*i)
   bool math;        // fast: always; parity: warps holding the hi lanes do the arithmetic, the others ferry lanes 64-127
-  float* scr;       // parity: exchange buffer of this thread's column-half group, [32][64]
+  float* scr;       // parity: exchange buffer of this thread's column group, [32][64]
   int64_t grow;     // global point index
   bool valid;
-  size_t tile;
   float x[3];       // input point (forward) or g-bar (tangent)
   float fb;         // f-bar (adjoint start)
   float fval;       // network output of this row (kept for the tanh mode)
 };
 
-__device__ __forceinline__ uint32_t img_off(int c0, int j, int row) {
-  return static_cast<uint32_t>(c0 / 8 + j) * kGranuleBytes + row * 16;
+// byte offset of (granule of column c, row) inside an operand image; c is a multiple of 8
+__device__ __forceinline__ uint32_t img_off(int c, int row) {
+  return static_cast<uint32_t>(c >> 3) * kGranuleBytes + row * 16;
 }
 
-// 32 columns of this thread's point -> A image in shared memory and / or a spill image in global memory
-template <int DT, bool PAR>
-__device__ __forceinline__ void store_chunk(const Epi& e, int c0, const float (&v)[32], uint8_t* img, bool to_smem) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (!PAR) {
-      const uint4 pk = pack8<DT>(&v[8 * j]);
-      const uint32_t off = img_off(c0, j, e.prow);
-      if (to_smem) st_smem_v4(e.sA + off, pk);
-      if (img) *reinterpret_cast<uint4*>(img + off) = pk;
-    } else {
-      float hi[8], lo[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        hi[t] = H16<DT>::rnd(v[8 * j + t]);
-        lo[t] = v[8 * j + t] - hi[t];
-      }
-      const uint4 ph = pack8<DT>(hi), pl = pack8<DT>(lo);
-      const uint32_t oh = img_off(c0, j, e.prow), ol = img_off(c0, j, e.prow + kParityPoints);
-      if (to_smem) { st_smem_v4(e.sA + oh, ph); st_smem_v4(e.sA + ol, pl); }
-      if (img) { *reinterpret_cast<uint4*>(img + oh) = ph; *reinterpret_cast<uint4*>(img + ol) = pl; }
-    }
-  }
-}
-template <int DT, bool PAR>
-__device__ __forceinline__ void load_chunk_global(const Epi& e, int c0, const uint8_t* img, float (&v)[32]) {
-  uint4 pk[4], pl[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    pk[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow));
-    if (PAR) pl[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow + kParityPoints));
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    unpack8<DT>(pk[j], &v[8 * j]);
-    if (PAR) unpack8_add<DT>(pl[j], &v[8 * j]);
-  }
-}
-template <int DT, bool PAR>
-__device__ __forceinline__ void load_chunk_smem(const Epi& e, int c0, float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    unpack8<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow)), &v[8 * j]);
-    if (PAR) unpack8_add<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow + kParityPoints)), &v[8 * j]);
-  }
-}
-__device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&b)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
-    b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
-  }
-}
-// 32 accumulator columns of this thread's point.  Parity: every thread of the column-half group must call (the
+// 32 accumulator columns of this thread's point.  Parity: every thread of the column group must call (the
 // threads of lanes 64-127 hand their half over through shared memory); only e.math threads get a result.
 template <bool PAR>
 __device__ __forceinline__ void load_acc32(const Epi& e, int c0, float (&v)[32]) {
@@ -227,18 +186,18 @@ __device__ __forceinline__ uint4 xblock_granule(const float (&x)[3], int h, floa
   return pack8<DT>(v);
 }
 
-// write granule e.h of a 16-column block for this thread's point (parity: the lo row of a block is zero, the split
-// lives in the columns) into shared memory and / or global memory
+// write granule g (0 / 1) of a 16-column block for this thread's point (parity: the lo row of a block is zero, the
+// split lives in the columns) into shared memory and / or global memory
 template <bool PAR>
-__device__ __forceinline__ void put_block(const Epi& e, const uint4& g, bool to_smem, uint8_t* gimg) {
-  const uint32_t off = e.h * kGranuleBytes + e.prow * 16;
+__device__ __forceinline__ void put_block(const Epi& e, int g, const uint4& v, bool to_smem, uint8_t* gimg) {
+  const uint32_t off = g * kGranuleBytes + e.prow * 16;
   const uint4 z = make_uint4(0, 0, 0, 0);
   if (to_smem) {
-    st_smem_v4(e.sA + off, g);
+    st_smem_v4(e.sA + off, v);
     if (PAR) st_smem_v4(e.sA + off + kParityPoints * 16, z);
   }
   if (gimg) {
-    *reinterpret_cast<uint4*>(gimg + off) = g;
+    *reinterpret_cast<uint4*>(gimg + off) = v;
     if (PAR) *reinterpret_cast<uint4*>(gimg + off + kParityPoints * 16) = z;
   }
 }
@@ -254,8 +213,9 @@ struct Bars {
 
 struct EpiConst {
   int H;
-  float beta, inv_beta, nbl2, ln2_over_beta;  // nbl2 = -beta*log2(e)
+  float beta, nbl2, ln2_over_beta;  // nbl2 = -beta*log2(e)
   bool relu;
+  bool no_math;  // FL_DBG_NO_MATH
 };
 
 // inputs / outputs of one step for this thread's tile
@@ -289,29 +249,30 @@ __device__ __forceinline__ float one_minus_dact(float a, const EpiConst& k) {
   return k.relu ? (a > 0.f ? 0.f : 1.f) : ex2_approx(a * k.nbl2);
 }
 
+// memory operands of one 16-column piece (two granules): hi rows, and lo rows in parity mode
 template <bool PAR>
-struct Packed32 {
-  uint4 h[4];
-  uint4 l[PAR ? 4 : 1];
+struct Piece {
+  uint4 h[2];
+  uint4 l[PAR ? 2 : 1];
 };
 template <bool PAR>
-__device__ __forceinline__ void ldg_chunk(const Epi& e, int c0, const uint8_t* img, Packed32<PAR>& pk) {
+__device__ __forceinline__ void ldg_piece(const Epi& e, int c, const uint8_t* img, Piece<PAR>& pk) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    pk.h[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow));
-    if (PAR) pk.l[j] = *reinterpret_cast<const uint4*>(img + img_off(c0, j, e.prow + kParityPoints));
+  for (int j = 0; j < 2; ++j) {
+    pk.h[j] = *reinterpret_cast<const uint4*>(img + img_off(c + 8 * j, e.prow));
+    if (PAR) pk.l[j] = *reinterpret_cast<const uint4*>(img + img_off(c + 8 * j, e.prow + kParityPoints));
   }
 }
 template <int DT, bool PAR>
-__device__ __forceinline__ void granule8(const Packed32<PAR>& pk, int j, float (&o)[8]) {
+__device__ __forceinline__ void granule8(const Piece<PAR>& pk, int j, float (&o)[8]) {
   unpack8<DT>(pk.h[j], o);
   if (PAR) unpack8_add<DT>(pk.l[j], o);
 }
-// 8 values of this thread's point -> one granule of a global image (parity: hi row and lo row)
+// 8 values of this thread's point -> the granule of column c of a global image (parity: hi row and lo row)
 template <int DT, bool PAR>
-__device__ __forceinline__ void stg_granule8(const Epi& e, uint8_t* img, int c0, int j, const float (&v)[8]) {
+__device__ __forceinline__ void stg_granule8(const Epi& e, uint8_t* img, int c, const float (&v)[8]) {
   if (!PAR) {
-    *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = pack8<DT>(v);
+    *reinterpret_cast<uint4*>(img + img_off(c, e.prow)) = pack8<DT>(v);
   } else {
     float hi[8], lo[8];
 #pragma unroll
@@ -319,18 +280,18 @@ __device__ __forceinline__ void stg_granule8(const Epi& e, uint8_t* img, int c0,
       hi[t] = H16<DT>::rnd(v[t]);
       lo[t] = v[t] - hi[t];
     }
-    *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = pack8<DT>(hi);
-    *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow + kParityPoints)) = pack8<DT>(lo);
+    *reinterpret_cast<uint4*>(img + img_off(c, e.prow)) = pack8<DT>(hi);
+    *reinterpret_cast<uint4*>(img + img_off(c, e.prow + kParityPoints)) = pack8<DT>(lo);
   }
 }
-
-// 8 values of this thread's point -> one granule of the A image in shared memory and (optionally) of a global image
+// 8 values of this thread's point -> the granule of column c of the A image in shared memory and (optionally) of a
+// global image
 template <int DT, bool PAR>
-__device__ __forceinline__ void put_granule8(const Epi& e, uint8_t* img, int c0, int j, const float (&v)[8]) {
+__device__ __forceinline__ void put_granule8(const Epi& e, uint8_t* img, int c, const float (&v)[8]) {
   if (!PAR) {
     const uint4 pk = pack8<DT>(v);
-    st_smem_v4(e.sA + img_off(c0, j, e.prow), pk);
-    if (img) *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = pk;
+    st_smem_v4(e.sA + img_off(c, e.prow), pk);
+    if (img) *reinterpret_cast<uint4*>(img + img_off(c, e.prow)) = pk;
   } else {
     float hi[8], lo[8];
 #pragma unroll
@@ -339,36 +300,36 @@ __device__ __forceinline__ void put_granule8(const Epi& e, uint8_t* img, int c0,
       lo[t] = v[t] - hi[t];
     }
     const uint4 ph = pack8<DT>(hi), pl = pack8<DT>(lo);
-    st_smem_v4(e.sA + img_off(c0, j, e.prow), ph);
-    st_smem_v4(e.sA + img_off(c0, j, e.prow + kParityPoints), pl);
+    st_smem_v4(e.sA + img_off(c, e.prow), ph);
+    st_smem_v4(e.sA + img_off(c, e.prow + kParityPoints), pl);
     if (img) {
-      *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow)) = ph;
-      *reinterpret_cast<uint4*>(img + img_off(c0, j, e.prow + kParityPoints)) = pl;
+      *reinterpret_cast<uint4*>(img + img_off(c, e.prow)) = ph;
+      *reinterpret_cast<uint4*>(img + img_off(c, e.prow + kParityPoints)) = pl;
     }
   }
 }
 
-// Operands of one 32-column chunk that come from memory: forward = the bias row (fp32, 8 floats per granule split
-// over xa.h[j] / xb.h[j]); other sweeps = the activation image (xa) and the q / u image (xb).
-template <int DT, bool PAR, int EPI>
-__device__ __forceinline__ void load_aux(const Epi& e, const StepIO& io, int c0, Packed32<PAR>& xa, Packed32<PAR>& xb) {
+// Operands of one 16-column piece that come from memory: forward = the bias row (fp32: granule j = xa.h[j] | xb.h[j]);
+// other sweeps = the activation image (xa) and the q / u image (xb).
+template <bool PAR, int EPI>
+__device__ __forceinline__ void load_aux(const Epi& e, const StepIO& io, int c, Piece<PAR>& xa, Piece<PAR>& xb) {
   if (EPI == EPI_FWD_HIDDEN) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      xa.h[j] = __ldg(reinterpret_cast<const uint4*>(io.vec + c0 + 8 * j));
-      xb.h[j] = __ldg(reinterpret_cast<const uint4*>(io.vec + c0 + 8 * j + 4));
+    for (int j = 0; j < 2; ++j) {
+      xa.h[j] = __ldg(reinterpret_cast<const uint4*>(io.vec + c + 8 * j));
+      xb.h[j] = __ldg(reinterpret_cast<const uint4*>(io.vec + c + 8 * j + 4));
     }
   } else {
-    ldg_chunk<PAR>(e, c0, io.in_a, xa);
-    if (io.in_b) ldg_chunk<PAR>(e, c0, io.in_b, xb);
+    ldg_piece<PAR>(e, c, io.in_a, xa);
+    if (io.in_b) ldg_piece<PAR>(e, c, io.in_b, xb);
   }
 }
 
 // The arithmetic of one granule (8 columns starting at column c) of a hidden-layer epilogue.
-// v: accumulator columns in, result out.  j: granule index inside the 32-column chunk the operands were loaded for.
+// v: accumulator columns in, result out.  j: granule index (0 / 1) inside the piece the operands were loaded for.
 template <int DT, bool PAR, int EPI>
 __device__ __forceinline__ void granule_math(const Epi& e, const StepIO& io, const EpiConst& k, int c, int j, float (&v)[8],
-                                             const Packed32<PAR>& xa, const Packed32<PAR>& xb, float* gskip) {
+                                             const Piece<PAR>& xa, const Piece<PAR>& xb, float* gskip) {
   const bool last = io.special && (c + 8 == k.H);  // columns H-3..H-1 carry the raw input (skip-in)
   if (EPI == EPI_FWD_HIDDEN) {
     // a_l = act(z_l + b_l)                                          reference model/networks.py:100-102
@@ -403,7 +364,7 @@ __device__ __forceinline__ void granule_math(const Epi& e, const StepIO& io, con
       granule8<DT, PAR>(xb, j, q);
 #pragma unroll
       for (int t = 0; t < 8; ++t) q[t] = k.beta * a[t] * q[t] * v[t];
-      stg_granule8<DT, PAR>(e, io.out_u, c, 0, q);
+      stg_granule8<DT, PAR>(e, io.out_u, c, q);
     }
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t] *= 1.f - a[t];
@@ -435,21 +396,23 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
   mbar_wait(&B.acc_full[0], par0);
   if (st.n_groups == 2) mbar_wait(&B.acc_full[1], par1);
   tc_fence_after();
-  const int nIt = k.H / 64;
-  for (int it = 0; it < nIt; ++it) {
-    const int c0 = it * 64 + e.h * 32;
+  for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
     float v[32];
     load_acc32<PAR>(e, c0, v);
     if (e.math) {
-      Packed32<PAR> xa, xb;
-      load_aux<DT, PAR, EPI>(e, io, c0, xa, xb);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float w[8];
+      for (int sub = 0; sub < 2; ++sub) {
+        Piece<PAR> xa, xb;
+        load_aux<PAR, EPI>(e, io, c0 + 16 * sub, xa, xb);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) w[t] = v[8 * j + t];
-        granule_math<DT, PAR, EPI>(e, io, k, c0 + 8 * j, j, w, xa, xb, gskip);
-        put_granule8<DT, PAR>(e, io.out, c0, j, w);
+        for (int j = 0; j < 2; ++j) {
+          float w[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) w[t] = v[16 * sub + 8 * j + t];
+          const int c = c0 + 16 * sub + 8 * j;
+          granule_math<DT, PAR, EPI>(e, io, k, c, j, w, xa, xb, gskip);
+          put_granule8<DT, PAR>(e, io.out, c, w);
+        }
       }
     }
   }
@@ -461,37 +424,31 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 // Hidden-layer epilogue, overlapped form (fast mode, H = 512: two accumulator halves of 256 columns).
 //   half 0 is processed while the MMAs of half 1 still read the A image, so its packed 16-bit result cannot go
 //   to shared memory yet: it is parked in TMEM, in the first 16 of the 32 accumulator columns the thread has just
 //   consumed.  Once half 1 is complete the parked columns move into the A image (-> a_lo: the next GEMM may start
 //   on K < 256 and overwrite accumulator half 0) and half 1 is processed straight into the A image (-> a_hi).
-// Latency hiding inside the two epilogue warps of each SM sub-partition: every spill-image line the step will read
-// is first requested into L2 (prefetch.global.L2, while the MMAs of the step are still running), the memory
-// operands travel through an NBUF-slot register ring filled NBUF chunks ahead of their use, and the TMEM reads are
-// double-buffered in 16-column pieces.
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
+// Each thread owns 2 chunks of 32 columns per half (4 pieces of 16).  Every spill-image line the step will read is
+// first requested into L2 (prefetch.global.L2, while the MMAs of the step are still running); the four epilogue
+// warps of an SM sub-partition cover each other's load latencies.
 template <int DT, int EPI>
 __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
-  // ring depth: forward (bias row, 32 registers per chunk) and reverse (one image, 16) cover a whole half; tangent
-  // and adjoint (two images, 32 per chunk, plus more live arithmetic) keep two chunks in flight
-  constexpr int NBUF = (EPI == EPI_REV_HIDDEN) ? 4 : 2;
   if (EPI != EPI_FWD_HIDDEN) {
-#pragma unroll 1
-    for (int ci = 0; ci < 8; ++ci) {
-      const int c0 = ci * 64 + e.h * 32;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        prefetch_l2(io.in_a + img_off(c0, j, e.prow));
-        if (io.in_b) prefetch_l2(io.in_b + img_off(c0, j, e.prow));
+        prefetch_l2(io.in_a + img_off(ci * 128 + e.h * 32 + 8 * j, e.prow));
+        if (io.in_b) prefetch_l2(io.in_b + img_off(ci * 128 + e.h * 32 + 8 * j, e.prow));
       }
     }
   }
-  Packed32<false> xa[NBUF], xb[NBUF];
-#pragma unroll
-  for (int it = 0; it < NBUF; ++it) load_aux<DT, false, EPI>(e, io, it * 64 + e.h * 32, xa[it], xb[it]);
+  Piece<false> xa, xb;
+  load_aux<false, EPI>(e, io, e.h * 32, xa, xb);
   mbar_wait(&B.acc_full[0], par0);
   tc_fence_after();
 #pragma unroll 1
@@ -500,17 +457,16 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       tmem_st_wait();
       mbar_wait(&B.acc_full[1], par1);
       tc_fence_after();
-#pragma unroll
-      for (int pair = 0; pair < 2; ++pair) {
+      {
         uint32_t r0[16], r1[16];
-        const int c0 = pair * 128 + e.h * 32;
+        const int c0 = e.h * 32;
         tmem_ld16(e.taddr + c0, r0);
-        tmem_ld16(e.taddr + c0 + 64, r1);
+        tmem_ld16(e.taddr + c0 + 128, r1);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          st_smem_v4(e.sA + img_off(c0, j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
-          st_smem_v4(e.sA + img_off(c0 + 64, j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
+          st_smem_v4(e.sA + img_off(c0 + 8 * j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
+          st_smem_v4(e.sA + img_off(c0 + 128 + 8 * j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
         }
       }
       fence_proxy_async_smem();
@@ -519,44 +475,36 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
         mbar_arrive(B.a_lo);
       }
     }
-    const int cbase = half * 256 + e.h * 32;
-    uint32_t r[2][16];
-    tmem_ld16(e.taddr + cbase, r[0]);
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      constexpr int kDummy = 0;
-      (void)kDummy;
-      const int slot = it % NBUF;
+    for (int pc = 0; pc < 4; ++pc) {
+      // piece pc of this half: chunk pc / 2, 16-column sub-piece pc % 2
+      const int c0 = half * 256 + (pc >> 1) * 128 + e.h * 32;  // chunk base column
+      const int c = c0 + (pc & 1) * 16;                        // first column of the piece
+      uint32_t r[16];
+      tmem_ld16(e.taddr + c, r);
+      if (pc > 0 || half == 1) load_aux<false, EPI>(e, io, c, xa, xb);
+      tmem_ld_wait();
+      uint32_t pk[8];
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c = cbase + it * 64 + sub * 16;  // first column of this 16-column piece
-        tmem_ld_wait();
-        if (!(it == 3 && sub == 1)) tmem_ld16(e.taddr + (sub == 0 ? c + 16 : c + 48), r[sub ^ 1]);
-        uint32_t pk[8];
+      for (int j = 0; j < 2; ++j) {
+        float w[8];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          float w[8];
+        for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r[8 * j + t]);
+        if (!k.no_math) granule_math<DT, false, EPI>(e, io, k, c + 8 * j, j, w, xa, xb, gskip);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r[sub][8 * jj + t]);
-          granule_math<DT, false, EPI>(e, io, k, c + 8 * jj, 2 * sub + jj, w, xa[slot], xb[slot], gskip);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) pk[4 * jj + t] = H16<DT>::pack(w[2 * t], w[2 * t + 1]);
-        }
-        const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (io.out) {
-          *reinterpret_cast<uint4*>(io.out + img_off(c, 0, e.prow)) = p0;
-          *reinterpret_cast<uint4*>(io.out + img_off(c, 1, e.prow)) = p1;
-        }
-        if (half == 0) {
-          tmem_st8(e.taddr + cbase + it * 64 + sub * 8, pk);
-        } else {
-          st_smem_v4(e.sA + img_off(c, 0, e.prow), p0);
-          st_smem_v4(e.sA + img_off(c, 1, e.prow), p1);
-        }
+        for (int t = 0; t < 4; ++t) pk[4 * j + t] = H16<DT>::pack(w[2 * t], w[2 * t + 1]);
       }
-      // refill this slot with the chunk NBUF positions ahead (chunk index = half * 4 + it)
-      if (half * 4 + it + NBUF < 8)
-        load_aux<DT, false, EPI>(e, io, (half * 4 + it + NBUF) * 64 + e.h * 32, xa[slot], xb[slot]);
+      const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if (io.out) {
+        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = p0;
+        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = p1;
+      }
+      if (half == 0) {
+        tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
+      } else {
+        st_smem_v4(e.sA + img_off(c, e.prow), p0);
+        st_smem_v4(e.sA + img_off(c + 8, e.prow), p1);
+      }
     }
   }
   fence_proxy_async_smem();
@@ -607,82 +555,86 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     mbar_init(B.a_hi, kEpiThreads);
     mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t ib = img_bytes(p.H);
 
-  // register file re-split (per SM sub-partition: 16384 registers = 1 light warp + 2 epilogue warps)
-  if (warp >= 8) {
+  // register file re-split (per SM sub-partition: 16384 registers = the CTA is launched with 640 x 96 registers; 128 x 40 + 512 x 104 fits that pool)
+  if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  if (warp == 8) {
-    // ------------------------------------------------------------------ weight producer
-    if (lane == 0) {
-      uint32_t stage = 0, round = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int s = 0; s < p.n_steps; ++s) {
-          const StepDesc& st = p.steps[s];
-          const int nchunks = st.n_groups * st.kchunks;
-          const uint8_t* src = p.wpack + st.w_off;
-          for (int c = 0; c < nchunks; ++c) {
-            mbar_wait(&w_empty[stage], (round & 1) ^ 1);
-            mbar_arrive_expect_tx(&w_full[stage], st.chunk_bytes);
-            bulk_g2s(sW + stage * kStageBytes, src + static_cast<size_t>(c) * st.chunk_bytes, st.chunk_bytes,
-                     &w_full[stage]);
-            if (++stage == NST) { stage = 0; ++round; }
-          }
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t stage = 0, round = 0, n0 = 0;
-      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int s = 0; s < p.n_steps; ++s) {
-          const StepDesc& st = p.steps[s];
-          if (st.n_groups == 0) continue;
-          const uint32_t par = n0 & 1;
-          const uint32_t idesc = make_idesc_f16(kTileRows, st.ng, DT == DT_BF16, false, false);
-          const uint32_t b_lbo = static_cast<uint32_t>(st.ng) * 16;
-          for (int g = 0; g < st.n_groups; ++g) {
-            for (int kc = 0; kc < st.kchunks; ++kc) {
-              if (g == 0) {
-                // the A image becomes available in two parts (hidden_step_staged)
-                if (kc == 0) {
-                  mbar_wait(B.a_lo, par);
-                  if (st.k_lo == 0) mbar_wait(B.a_hi, par);
-                  tc_fence_after();
-                } else if (kc == st.k_lo) {
-                  mbar_wait(B.a_hi, par);
-                  tc_fence_after();
-                }
+    if (warp == kProducerWarp) {
+      // ------------------------------------------------------------------ weight producer
+      if (lane == 0) {
+        uint32_t stage = 0, round = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+          for (int s = 0; s < p.n_steps; ++s) {
+            const StepDesc& st = p.steps[s];
+            const int nchunks = st.n_groups * st.kchunks;
+            const uint8_t* src = p.wpack + st.w_off;
+            for (int c = 0; c < nchunks; ++c) {
+              mbar_wait(&w_empty[stage], (round & 1) ^ 1);
+              if (p.flags & FL_DBG_NO_W) {
+                mbar_arrive(&w_full[stage]);
+              } else {
+                mbar_arrive_expect_tx(&w_full[stage], st.chunk_bytes);
+                bulk_g2s(sW + stage * kStageBytes, src + static_cast<size_t>(c) * st.chunk_bytes, st.chunk_bytes,
+                         &w_full[stage]);
               }
-              mbar_wait(&w_full[stage], round & 1);
-              tc_fence_after();
-              const uint32_t a_addr = sA_u + static_cast<uint32_t>((kc % st.a_chunks) * st.k16 * 2) * kGranuleBytes;
-              const uint32_t b_addr = sW_u + stage * kStageBytes;
-              for (int k = 0; k < st.k16; ++k) {
-                const uint64_t da = make_smem_desc(a_addr + k * 2 * kGranuleBytes, kGranuleBytes, 128);
-                const uint64_t db = make_smem_desc(b_addr + k * 2 * b_lbo, b_lbo, 128);
-                umma_f16_ss(tmem_base + g * st.ng, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
-              }
-              umma_commit(&w_empty[stage]);
               if (++stage == NST) { stage = 0; ++round; }
             }
-            umma_commit(&B.acc_full[g]);
           }
-          ++n0;
+        }
+      }
+    } else if (warp == kMmaWarp) {
+      // ------------------------------------------------------------------ MMA issuer
+      if (lane == 0) {
+        uint32_t stage = 0, round = 0, n0 = 0;
+        const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+          for (int s = 0; s < p.n_steps; ++s) {
+            const StepDesc& st = p.steps[s];
+            if (st.n_groups == 0) continue;
+            const uint32_t par = n0 & 1;
+            const uint32_t idesc = make_idesc_f16(kTileRows, st.ng, DT == DT_BF16, false, false);
+            const uint32_t b_lbo = static_cast<uint32_t>(st.ng) * 16;
+            for (int g = 0; g < st.n_groups; ++g) {
+              for (int kc = 0; kc < st.kchunks; ++kc) {
+                if (g == 0) {
+                  // the A image becomes available in two parts (hidden_step_staged)
+                  if (kc == 0) {
+                    mbar_wait(B.a_lo, par);
+                    if (st.k_lo == 0) mbar_wait(B.a_hi, par);
+                    tc_fence_after();
+                  } else if (kc == st.k_lo) {
+                    mbar_wait(B.a_hi, par);
+                    tc_fence_after();
+                  }
+                }
+                mbar_wait(&w_full[stage], round & 1);
+                tc_fence_after();
+                const uint32_t a_addr = sA_u + static_cast<uint32_t>((kc % st.a_chunks) * st.k16 * 2) * kGranuleBytes;
+                const uint32_t b_addr = sW_u + stage * kStageBytes;
+                for (int k = 0; k < st.k16; ++k) {
+                  const uint64_t da = make_smem_desc(a_addr + k * 2 * kGranuleBytes, kGranuleBytes, 128);
+                  const uint64_t db = make_smem_desc(b_addr + k * 2 * b_lbo, b_lbo, 128);
+                  if (!(p.flags & FL_DBG_NO_MMA)) umma_f16_ss(tmem_base + g * st.ng, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&w_empty[stage]);
+                if (++stage == NST) { stage = 0; ++round; }
+              }
+              umma_commit(&B.acc_full[g]);
+            }
+            ++n0;
+          }
         }
       }
     }
-  }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     Epi e;
     e.sA = smem_u32(sA);
     const int q = warp & 3;
@@ -697,12 +649,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     EpiConst k;
     k.H = p.H;
     k.beta = p.beta;
-    k.inv_beta = p.inv_beta;
     k.nbl2 = -p.beta * 1.4426950408889634f;
     k.ln2_over_beta = 0.6931471805599453f * p.inv_beta;
     k.relu = (p.flags & FL_RELU) != 0;
+    k.no_math = (p.flags & FL_DBG_NO_MATH) != 0;
     const bool relu = k.relu;
-    const int nIt = p.H / 64;
     const float mult = p.seed_mult ? __ldg(p.seed_mult) : 1.f;
     // layer whose image carries the raw input in its last three columns (feeds the skip layer): those columns have no
     // activation state, their derivative factor must read as 0
@@ -710,10 +661,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     const bool has_u = (p.flags & FL_TANGENT) && !relu;
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      e.tile = tile;
       e.grow = static_cast<int64_t>(tile) * PTS + e.prow;
       e.valid = e.grow < p.n;
-      // ---------------------------------------------------------------- prologue: input block
+      // ---------------------------------------------------------------- prologue: input block (column groups 0, 1
+      // write its two granules)
       const int first = p.steps[0].epi;
       e.x[0] = e.x[1] = e.x[2] = 0.f;
       if (first == EPI_FWD_HIDDEN) {
@@ -747,9 +698,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               for (int j = 0; j < 3; ++j) e.x[j] = -1.f + (2.f * static_cast<float>(ci[j]) + 1.f) * hs;
             }
           }
-          const uint4 gx = xblock_granule<DT>(e.x, e.h, 1.f);
-          put_block<PAR>(e, gx, true,
-                         (p.flags & FL_SPILL_X) ? p.Ximg + tile * static_cast<size_t>(2 * kGranuleBytes) : nullptr);
+          if (e.h < 2) {
+            const uint4 gx = xblock_granule<DT>(e.x, e.h, 1.f);
+            put_block<PAR>(e, e.h, gx, true,
+                           (p.flags & FL_SPILL_X) ? p.Ximg + tile * static_cast<size_t>(2 * kGranuleBytes) : nullptr);
+          }
         }
       } else {
         // tangent / adjoint program: seeds
@@ -764,14 +717,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           } else {
             e.fb = 0.f;
           }
-          const uint4 gg = xblock_granule<DT>(e.x, e.h, 0.f);
-          put_block<PAR>(e, gg, true, p.Gimg + tile * static_cast<size_t>(2 * kGranuleBytes));
-          // f-bar block: cols 0-2 = fbar hi/lo/lolo, col 15 = 1
-          float fh, fl, fll;
-          split3<DT>(e.fb, fh, fl, fll);
-          float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (e.h == 0) { sv[0] = fh; sv[1] = fl; sv[2] = fll; } else { sv[7] = e.valid ? 1.f : 0.f; }
-          put_block<PAR>(e, pack8<DT>(sv), false, p.Simg + tile * static_cast<size_t>(2 * kGranuleBytes));
+          if (e.h < 2) {
+            const uint4 gg = xblock_granule<DT>(e.x, e.h, 0.f);
+            put_block<PAR>(e, e.h, gg, true, p.Gimg + tile * static_cast<size_t>(2 * kGranuleBytes));
+            // f-bar block: cols 0-2 = fbar hi/lo/lolo, col 15 = 1
+            float fh, fl, fll;
+            split3<DT>(e.fb, fh, fl, fll);
+            float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (e.h == 0) { sv[0] = fh; sv[1] = fl; sv[2] = fll; } else { sv[7] = e.valid ? 1.f : 0.f; }
+            put_block<PAR>(e, e.h, pack8<DT>(sv), false, p.Simg + tile * static_cast<size_t>(2 * kGranuleBytes));
+          }
         }
       }
       fence_proxy_async_smem();
@@ -815,19 +770,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             // q_{L-1} = w_L * act'(z_{L-1}); the A image still holds a_{L-1}
             uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l, p.n_tiles, tile, ib) : nullptr;
             if (e.math) {
-              for (int it = 0; it < nIt; ++it) {
-                const int c0 = it * 64 + e.h * 32;
+              for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                  const int c = c0 + 8 * j;
                   float a[8];
-                  unpack8<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow)), a);
-                  if (PAR) unpack8_add<DT>(ld_smem_v4(e.sA + img_off(c0, j, e.prow + kParityPoints)), a);
-                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j));
-                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j + 4));
+                  unpack8<DT>(ld_smem_v4(e.sA + img_off(c, e.prow)), a);
+                  if (PAR) unpack8_add<DT>(ld_smem_v4(e.sA + img_off(c, e.prow + kParityPoints)), a);
+                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_last + c));
+                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_last + c + 4));
                   const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                   for (int t = 0; t < 8; ++t) a[t] = w[t] * (1.f - one_minus_dact(a[t], k));
-                  put_granule8<DT, PAR>(e, qimg, c0, j, a);
+                  put_granule8<DT, PAR>(e, qimg, c, a);
                 }
               }
             }
@@ -849,7 +804,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             mbar_wait(&B.acc_full[0], n0 & 1);
             tc_fence_after();
             ++n0;
-            named_bar_sync(1, kEpiThreads);  // gskip written by the h=1 warps of an earlier step
+            named_bar_sync(1, kEpiThreads);  // gskip written by the last column group in an earlier step
             if (e.h == 0) {
               float v[32];
               load_acc32<PAR>(e, 0, v);
@@ -883,27 +838,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
             uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
             if (e.math) {
-              for (int it = 0; it < nIt; ++it) {
-                const int c0 = it * 64 + e.h * 32;
-                Packed32<PAR> xa, xu;
-                ldg_chunk<PAR>(e, c0, aimg, xa);
-                if (has_u) ldg_chunk<PAR>(e, c0, uimg, xu);
+              for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float a[8];
-                  granule8<DT, PAR>(xa, j, a);
-                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j));
-                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_last + c0 + 8 * j + 4));
-                  const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                for (int sub = 0; sub < 2; ++sub) {
+                  Piece<PAR> xa, xu;
+                  ldg_piece<PAR>(e, c0 + 16 * sub, aimg, xa);
+                  if (has_u) ldg_piece<PAR>(e, c0 + 16 * sub, uimg, xu);
 #pragma unroll
-                  for (int t = 0; t < 8; ++t) a[t] = (1.f - one_minus_dact(a[t], k)) * (w[t] * e.fb);
-                  if (has_u) {
-                    float u[8];
-                    granule8<DT, PAR>(xu, j, u);
+                  for (int j = 0; j < 2; ++j) {
+                    const int c = c0 + 16 * sub + 8 * j;
+                    float a[8];
+                    granule8<DT, PAR>(xa, j, a);
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_last + c));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_last + c + 4));
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) a[t] += u[t];
+                    for (int t = 0; t < 8; ++t) a[t] = (1.f - one_minus_dact(a[t], k)) * (w[t] * e.fb);
+                    if (has_u) {
+                      float u[8];
+                      granule8<DT, PAR>(xu, j, u);
+#pragma unroll
+                      for (int t = 0; t < 8; ++t) a[t] += u[t];
+                    }
+                    put_granule8<DT, PAR>(e, zimg, c, a);
                   }
-                  put_granule8<DT, PAR>(e, zimg, c0, j, a);
                 }
               }
             }
@@ -929,7 +887,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -61,6 +61,10 @@ enum : uint32_t {
   FL_SPILL_X = 1u << 2,   // write the input-block image (training, for dW_0 / biases)
   FL_TANGENT = 1u << 3,   // TA kernel: run the tangent sweep (second-order terms present)
   FL_RELU = 1u << 4,      // ReLU hidden activation + tanh output (beta == 0 in the reference ini)
+  // measurement-only switches (SDFNET_DEBUG_FLAGS environment variable; results are wrong when set)
+  FL_DBG_NO_MMA = 1u << 16,   // MMA issuer waits / commits but issues no tcgen05.mma
+  FL_DBG_NO_MATH = 1u << 17,  // hidden-layer epilogues skip their arithmetic and stores
+  FL_DBG_NO_W = 1u << 18,     // weight producer signals the ring without copying
 };
 
 struct ChainParams {
