@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdfnet.so")
+# SDFNET_LIB selects another build of the same sources (tools/build_prof.sh: the cycle-counter measurement build)
+LIB_PATH = os.environ.get("SDFNET_LIB") or os.path.join(_HERE, "libsdfnet.so")
 
 c_void_p = ctypes.c_void_p
 c_int32 = ctypes.c_int32

@@ -65,6 +65,9 @@ enum : uint32_t {
   FL_DBG_NO_MMA = 1u << 16,   // MMA issuer waits / commits but issues no tcgen05.mma
   FL_DBG_NO_MATH = 1u << 17,  // hidden-layer epilogues skip their arithmetic and stores
   FL_DBG_NO_W = 1u << 18,     // weight producer signals the ring without copying
+  FL_DBG_NO_MUFU = 1u << 19,  // ex2 / lg2 replaced by plain arithmetic
+  FL_DBG_NO_AUX = 1u << 20,   // spill-image / bias operands of the hidden epilogues are not loaded
+  FL_DBG_NO_STG = 1u << 21,   // hidden epilogues do not store their spill images
 };
 
 struct ChainParams {
@@ -103,6 +106,9 @@ struct ChainParams {
   uint8_t* Gimg;           // [tile][2 granules]  g-bar split block
   uint8_t* Simg;           // [tile][2 granules]  f-bar split block (+ ones column)
   uint32_t flags;
+#ifdef SDF_CLOCKS
+  long long* dbg_clk;      // measurement build only: [8 epilogue kinds][8] cycle counters of thread 0, summed over CTAs
+#endif
 };
 
 // one unit of work of the weight-gradient kernel:  out[n][m] += sum_tiles  A1^T B1 (+ A2^T B2)
