@@ -16,7 +16,7 @@ DTYPE_IDS = {"bf16": 0, "fp16": 1}
 PRECISION_IDS = {"fast": 0, "parity": 1}
 
 # default cap of the spill workspace of one training chunk (bytes); SDFNET_WS_GB overrides
-_WS_CAP_BYTES = int(float(os.environ.get("SDFNET_WS_GB", "24")) * (1 << 30))
+_WS_CAP_BYTES = int(float(os.environ.get("SDFNET_WS_GB", "64")) * (1 << 30))
 
 
 def _ptr(t):
