@@ -16,6 +16,7 @@ cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* d
                                 int k16, int kind, float scale, int dtype, int split, cudaStream_t stream);
 cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream);
 cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
+cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
                              float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
                              int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
@@ -100,6 +101,7 @@ struct sdfnet_handle {
   DwItem* items_dev = nullptr;
   int items_cap = 0;
   int items_n = 0;                 // cached work list: valid for (items_ws, items_tiles, items_so)
+  int items_pair_n = 0;            // the first items_pair_n entries are 256 x 256 blocks for the CTA-pair kernel
   const void* items_ws = nullptr;
   int items_tiles = -1;
   int items_so = -1;
@@ -486,26 +488,63 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   const uint32_t ib = img_bytes(H);
   const uint32_t xb = 2 * kGranuleBytes;
   const GradLayout& gl = h->gl;
-  if (h->items_ws == s.A && h->items_tiles == tiles && h->items_so == (second_order ? 1 : 0) && h->items_n > 0) {
-    Launch lr(h, PC_DW, stream);
-    CU(launch_dw(h->items_dev, h->items_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+  auto launch_both = [&]() -> int {
+    Launch lr(h, PC_DW, stream, h->items_pair_n > 0 && h->items_n > h->items_pair_n ? 2 : 1);
+    if (h->items_pair_n > 0)
+      CU(launch_dw2(h->items_dev, h->items_pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+    if (h->items_n > h->items_pair_n)
+      CU(launch_dw(h->items_dev + h->items_pair_n, h->items_n - h->items_pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
     return 0;
-  }
+  };
+  if (h->items_ws == s.A && h->items_tiles == tiles && h->items_so == (second_order ? 1 : 0) && h->items_n > 0) return launch_both();
   std::vector<DwItem> items;
   const int nmb = H / 128 > 0 ? H / 128 : 1;
   if (H % 128) return fail(1, "training requires hidden width multiple of 128 (got %d)", H);
+  const size_t arr = static_cast<size_t>(ib) * tiles;  // bytes of one layer of one spill array
+  auto split_range = [&](int sp, int ksplit, uint32_t& t0, uint32_t& t1) {
+    t0 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * sp / ksplit);
+    t1 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * (sp + 1) / ksplit);
+  };
+  int pair_n = 0;
+  const bool use_pairs = H % 256 == 0;
+  if (use_pairs) {
+    // 256 x 256 blocks of dW_l for the CTA-pair kernel (dw2_kernel)
+    const int nb2 = H / 256;
+    const int types = (L - 1) * nb2 * nb2;
+    int ksplit = (8 * (h->num_sms / 2) + types - 1) / types;
+    if (ksplit > tiles) ksplit = tiles;
+    if (ksplit < 1) ksplit = 1;
+    for (int sp = 0; sp < ksplit; ++sp) {
+      uint32_t t0, t1;
+      split_range(sp, ksplit, t0, t1);
+      if (t1 <= t0) continue;
+      for (int l = 1; l < L; ++l)
+        for (int mb = 0; mb < nb2; ++mb)
+          for (int nh = 0; nh < nb2; ++nh) {
+            DwItem d{};
+            d.A1 = s.Z + arr * l;        d.B1 = s.A + arr * (l - 1);
+            if (second_order) { d.A2 = s.Q + arr * l; d.B2 = s.AD + arr * (l - 1); }
+            d.a_tstride = ib; d.b_tstride = ib;
+            d.a_off = static_cast<uint32_t>(mb) * 32 * kGranuleBytes;
+            d.b_off = static_cast<uint32_t>(nh) * 32 * kGranuleBytes;
+            d.n = 256; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1;
+            d.out = gl.main_acc + (static_cast<size_t>(l - 1) * H + static_cast<size_t>(nh) * 256) * H + mb * 256;
+            items.push_back(d);
+          }
+    }
+    pair_n = static_cast<int>(items.size());
+  }
   const int nb = H > 256 ? 256 : H;       // N per main item
   const int nnh = H / nb;
-  const int types = (L - 1) * nmb * nnh + (L + 3) * nmb;
+  const int types = (use_pairs ? 0 : (L - 1) * nmb * nnh) + (L + 3) * nmb;
   int ksplit = (8 * h->num_sms + types - 1) / types;
   if (ksplit > tiles) ksplit = tiles;
   if (ksplit < 1) ksplit = 1;
-  const size_t arr = static_cast<size_t>(ib) * tiles;  // bytes of one layer of one spill array
   for (int sp = 0; sp < ksplit; ++sp) {
-    const uint32_t t0 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * sp / ksplit);
-    const uint32_t t1 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * (sp + 1) / ksplit);
+    uint32_t t0, t1;
+    split_range(sp, ksplit, t0, t1);
     if (t1 <= t0) continue;
-    for (int l = 1; l < L; ++l) {
+    for (int l = 1; l < L && !use_pairs; ++l) {
       for (int mb = 0; mb < nmb; ++mb)
         for (int nh = 0; nh < nnh; ++nh) {
           DwItem d{};
@@ -558,10 +597,8 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   // the list is rebuilt per call from a pageable host vector: a synchronous copy keeps it simple and safe
   CU(cudaMemcpyAsync(h->items_dev, items.data(), sizeof(DwItem) * n_items, cudaMemcpyHostToDevice, stream));
   CU(cudaStreamSynchronize(stream));
-  h->items_n = n_items; h->items_ws = s.A; h->items_tiles = tiles; h->items_so = second_order ? 1 : 0;
-  Launch lr(h, PC_DW, stream);
-  CU(launch_dw(h->items_dev, n_items, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
-  return 0;
+  h->items_n = n_items; h->items_pair_n = pair_n; h->items_ws = s.A; h->items_tiles = tiles; h->items_so = second_order ? 1 : 0;
+  return launch_both();
 }
 
 // forward (+reverse) over one chunk, spilling what training needs

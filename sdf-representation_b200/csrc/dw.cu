@@ -159,4 +159,175 @@ cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parit
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2): one pair owns a 256 x 256 block of dW.
+// Each CTA loads the 128-feature half of the A block that its TMEM lanes accumulate and one 128-feature half of the
+// B block (the tensor cores of the pair read both halves), i.e. 64 KB per tile and term instead of 96 KB for a
+// 128 x 256 block: half the L2 -> SM bytes and half the shared-memory traffic per FLOP of dw_kernel.
+// Warp roles per CTA (192 threads): warps 0-3 epilogue, warp 4 producer, warp 5 = MMA issuer in the leader CTA
+// (rank 0) and "my half has landed" relay in the peer CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDw2Stages = 3;
+constexpr uint32_t kDw2Half = 16 * kGranuleBytes;        // 128 features x 128 points
+constexpr uint32_t kDw2StageBytes = 2 * kDw2Half;        // A half + B half
+constexpr uint32_t kDw2Smem = kDw2Stages * kDw2StageBytes + 256;
+
+template <int DT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1)
+dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDw2Stages * kDw2StageBytes);
+  uint64_t* full = bars;                         // [3] local: this CTA's halves have landed
+  uint64_t* empty = bars + kDw2Stages;           // [3] both CTAs: the pair's MMAs on this stage are done
+  uint64_t* peer_full = bars + 2 * kDw2Stages;   // [3] leader only: the peer's halves have landed
+  uint64_t* acc_full = bars + 3 * kDw2Stages;    // [2] both CTAs
+  uint64_t* acc_empty = acc_full + 2;            // [2] leader only: both epilogues drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kDw2Stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&peer_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 256);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc2<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits and the TMEM allocation of both CTAs are in place
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t stage = 0, round = 0;
+      for (int it = pair; it < n_items; it += n_pairs) {
+        const DwItem d = items[it];
+        const int nterms = d.A2 ? 2 : 1;
+        for (uint32_t tile = d.tile0; tile < d.tile1; ++tile) {
+          for (int term = 0; term < nterms; ++term) {
+            const uint8_t* a = (term ? d.A2 : d.A1) + static_cast<size_t>(tile) * d.a_tstride + d.a_off + rank * kDw2Half;
+            const uint8_t* b = (term ? d.B2 : d.B1) + static_cast<size_t>(tile) * d.b_tstride + d.b_off + rank * kDw2Half;
+            mbar_wait(&empty[stage], (round & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[stage], kDw2StageBytes);
+            uint8_t* dst = smem + stage * kDw2StageBytes;
+            bulk_g2s(dst, a, kDw2Half, &full[stage]);
+            bulk_g2s(dst + kDw2Half, b, kDw2Half, &full[stage]);
+            if (++stage == kDw2Stages) { stage = 0; ++round; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      uint32_t stage = 0, round = 0, item_cnt = 0;
+      if (rank != 0) {
+        // relay: tell the leader when this CTA's halves of a stage are in shared memory
+        for (int it = pair; it < n_items; it += n_pairs) {
+          const DwItem d = items[it];
+          const uint32_t uses = (d.tile1 - d.tile0) * (d.A2 ? 2u : 1u);
+          for (uint32_t u = 0; u < uses; ++u) {
+            mbar_wait(&full[stage], round & 1);
+            mbar_arrive_cluster(&peer_full[stage], 0);
+            if (++stage == kDw2Stages) { stage = 0; ++round; }
+          }
+        }
+      } else {
+        const uint32_t lbo = 128u;            // K-group (8 image rows) stride
+        const uint32_t sbo = kGranuleBytes;   // MN-block (8 features) stride
+        const uint32_t idesc = make_idesc_f16(256, 256, DT == DT_BF16, true, true);
+        for (int it = pair; it < n_items; it += n_pairs, ++item_cnt) {
+          const DwItem d = items[it];
+          const uint32_t as = item_cnt & 1;
+          mbar_wait_cluster(&acc_empty[as], ((item_cnt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const int nterms = d.A2 ? 2 : 1;
+          uint32_t first = 1;
+          for (uint32_t tile = d.tile0; tile < d.tile1; ++tile) {
+            for (int term = 0; term < nterms; ++term) {
+              mbar_wait(&full[stage], round & 1);
+              mbar_wait_cluster(&peer_full[stage], round & 1);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(smem + stage * kDw2StageBytes);
+              const uint32_t b_addr = a_addr + kDw2Half;
+              const uint64_t da0 = make_smem_desc(a_addr, lbo, sbo), db0 = make_smem_desc(b_addr, lbo, sbo);
+              if (!parity) {
+#pragma unroll
+                for (int k = 0; k < kTileRows / 16; ++k) {
+                  umma_f16_ss2(tmem_base + as * 256, da0 + static_cast<uint64_t>(k) * 16, db0 + static_cast<uint64_t>(k) * 16, idesc,
+                               first ? 0u : 1u);
+                  first = 0;
+                }
+              } else {
+                // image rows 0-63 = hi parts, 64-127 = lo parts of the same 64 points: hi.hi + lo.hi + hi.lo
+#pragma unroll
+                for (int k = 0; k < kParityPoints / 16; ++k) {
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) {
+                    const uint32_t ka = k + (c == 1 ? 4 : 0), kb = k + (c == 2 ? 4 : 0);
+                    umma_f16_ss2(tmem_base + as * 256, da0 + static_cast<uint64_t>(ka) * 16, db0 + static_cast<uint64_t>(kb) * 16, idesc,
+                                 first ? 0u : 1u);
+                    first = 0;
+                  }
+                }
+              }
+              umma_commit2(&empty[stage], 3);
+              if (++stage == kDw2Stages) { stage = 0; ++round; }
+            }
+          }
+          umma_commit2(&acc_full[as], 3);
+        }
+      }
+    }
+  } else {
+    uint32_t item_cnt = 0;
+    const int m = static_cast<int>(rank) * 128 + warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int it = pair; it < n_items; it += n_pairs, ++item_cnt) {
+      const DwItem d = items[it];
+      const uint32_t as = item_cnt & 1;
+      mbar_wait(&acc_full[as], (item_cnt >> 1) & 1);
+      tc_fence_after();
+      if (d.tile1 > d.tile0) {
+        const float im = d.inv_mult ? __ldg(d.inv_mult) : 1.f;
+        for (uint32_t c0 = 0; c0 < 256; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + as * 256 + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(d.out + static_cast<size_t>(c0 + j) * d.out_ld + m, __uint_as_float(r[j]) * im);
+        }
+      }
+      tc_fence_before();
+      if (rank == 0) mbar_arrive(&acc_empty[as]);
+      else mbar_arrive_cluster(&acc_empty[as], 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared memory and TMEM stay valid until both CTAs are done
+  if (warp == 5) tmem_dealloc2<512>(tmem_base);
+}
+
+cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream) {
+  static bool attr_set[2] = {false, false};
+  auto kfn = dtype == DT_BF16 ? dw2_kernel<DT_BF16> : dw2_kernel<DT_FP16>;
+  if (!attr_set[dtype]) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDw2Smem));
+    if (e != cudaSuccess) return e;
+    attr_set[dtype] = true;
+  }
+  if (n_items <= 0) return cudaSuccess;
+  int pairs = num_sms / 2;
+  if (n_items < pairs) pairs = n_items;
+  kfn<<<2 * pairs, kDwThreads, kDw2Smem, stream>>>(items_dev, n_items, parity);
+  return cudaGetLastError();
+}
+
 }  // namespace sdf

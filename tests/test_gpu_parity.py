@@ -295,6 +295,36 @@ def test_linearity_of_parameter_gradients():
     assert e < 2e-2
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("hidden,skip", [(256, 2), (512, 0)])
+def test_pair_dw_kernel_matches_oracle(hidden, skip, mode):
+    """Widths that are multiples of 256 take the CTA-pair weight-gradient kernel (dw2_kernel, tcgen05 cta_group::2):
+    every parameter-gradient tensor of an IGRLOSS step against the fp64 oracle, ragged batch (tail tile, several
+    split-K ranges)."""
+    import sdf_representation_b200 as pkg
+
+    torch.manual_seed(11)
+    L = 3
+    sk = (skip,) if skip else ()
+    net = pkg.ImplicitNet(3, [hidden] * L, sk, 100.0, True, precision=mode).to(dev())
+    n = 3001
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(n, 3, generator=g) * 2 - 1
+    y = orc.torus_labels(x)
+    W = [getattr(net, f"lin{i}").weight.detach().double().cpu() for i in range(L + 1)]
+    b = [getattr(net, f"lin{i}").bias.detach().double().cpu() for i in range(L + 1)]
+    loss_ref, _, dW, db = orc.igr_loss_and_grads(W, b, x.double(), y.double(), sk, 100.0)
+    loss = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)(x.to(dev()), y.float().to(dev()), net, 0)
+    loss.backward()
+    worst = 0.0
+    for i in range(L + 1):
+        lin = getattr(net, f"lin{i}")
+        worst = max(worst, rel_err(lin.weight.grad.cpu(), dW[i].float()), rel_err(lin.bias.grad.cpu(), db[i].float()))
+    print(f"pair dW H={hidden} {mode}: loss {float(loss):.6f} vs {float(loss_ref):.6f}, worst grad rel err {worst:.3e}")
+    assert abs(float(loss) - float(loss_ref)) < (5e-5 if mode == "parity" else 5e-3)
+    assert worst < TOL_GRAD_REL[mode]
+
+
 def test_octree_bit_exact_given_gpu_sdf():
     from sdf_representation_b200 import inference
 
