@@ -292,8 +292,9 @@ static void add_step(ChainParams& p, int epi, int layer, const StepImage* img) {
   } else {
     s.n_groups = 0; s.ng = 0; s.kchunks = 0; s.k16 = 0; s.a_chunks = 1; s.chunk_bytes = 0; s.w_off = 0;
   }
-  // A columns [0,256) of a 512-wide image are released first (chain.cu hidden_step_staged)
-  s.k_lo = (img && img->a_chunks > 1 && img->k16 * 16 * img->a_chunks > 256) ? 256 / (img->k16 * 16) : 0;
+  // a 512-wide A image is released in four 128-column quarters (chain.cu hidden_step_staged): k_lo = weight chunks per
+  // quarter; 0 = the step waits for the whole image before its first MMA
+  s.k_lo = (img && img->a_chunks % 4 == 0 && img->k16 * 16 * img->a_chunks == 512) ? img->a_chunks / 4 : 0;
   s.signal = 0;
 }
 // a step's A image is consumed iff the next step of the program is a GEMM

@@ -224,9 +224,12 @@ __device__ __forceinline__ void put_block(const Epi& e, int g, const uint4& v, b
 // ------------------------------------------------------------------------------------------------
 struct Bars {
   uint64_t* acc_full;  // [2]  MMA issuer -> epilogue: accumulator half g is complete
-  uint64_t* a_lo;      //      epilogue -> MMA issuer: A-image columns [0,256) (or all, H <= 256) are in place
-  uint64_t* a_hi;      //      epilogue -> MMA issuer: A-image columns [256,512) are in place
+  uint64_t* a_q;       // [4]  epilogue -> MMA issuer: A-image columns [128 j, 128 j + 128) are in place
 };
+__device__ __forceinline__ void arrive_all_quarters(const Bars& B) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mbar_arrive(&B.a_q[j]);
+}
 
 struct EpiConst {
   int H;
@@ -537,8 +540,7 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
   fence_proxy_async_smem();
   if (st.signal) {
     tc_fence_before();
-    mbar_arrive(B.a_lo);
-    mbar_arrive(B.a_hi);
+    arrive_all_quarters(B);
   }
 }
 
@@ -547,8 +549,9 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("pre
 // Hidden-layer epilogue, overlapped form (fast mode, H = 512: two accumulator halves of 256 columns).
 //   half 0 is processed while the MMAs of half 1 still read the A image, so its packed 16-bit result cannot go
 //   to shared memory yet: it is parked in TMEM, in the first 16 of the 32 accumulator columns the thread has just
-//   consumed.  Once half 1 is complete the parked columns move into the A image (-> a_lo: the next GEMM may start
-//   on K < 256 and overwrite accumulator half 0) and half 1 is processed straight into the A image (-> a_hi).
+//   consumed.  Once half 1 is complete the parked columns move into the A image (-> quarters 0, 1 released: the
+//   next GEMM may start on K < 256 and overwrite accumulator half 0) and half 1 is processed straight into the A
+//   image (-> quarter 2 released half-way, quarter 3 at the end).
 // Each thread owns 2 chunks of 32 columns per half (4 pieces of 16).  Every spill-image line the step will read is
 // first requested into L2 (prefetch.global.L2, while the MMAs of the step are still running); the four epilogue
 // warps of an SM sub-partition cover each other's load latencies.
@@ -599,7 +602,8 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       fence_proxy_async_smem();
       if (st.signal) {
         tc_fence_before();
-        mbar_arrive(B.a_lo);
+        mbar_arrive(&B.a_q[0]);
+        mbar_arrive(&B.a_q[1]);
       }
       CLK_MARK(EPI, 3);
     }
@@ -648,13 +652,18 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       } else {
         st_smem_v4(e.sA + img_off(c, e.prow), p0);
         st_smem_v4(e.sA + img_off(c + 8, e.prow), p1);
+        if (pc == 1) {
+          // this thread's share of A columns [256,384) is written: the next GEMM may run two more weight chunks
+          fence_proxy_async_smem();
+          if (st.signal) mbar_arrive(&B.a_q[2]);
+        }
       }
     }
   }
   fence_proxy_async_smem();
   if (st.signal) {
     tc_fence_before();
-    mbar_arrive(B.a_hi);
+    mbar_arrive(&B.a_q[3]);
   }
   CLK_MARK(EPI, 4);
 #ifdef SDF_CLOCKS
@@ -684,9 +693,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   uint64_t* w_empty = bars + NST;     // [NST]
   Bars B;
   B.acc_full = bars + 2 * NST;        // [2]
-  B.a_lo = bars + 2 * NST + 2;
-  B.a_hi = bars + 2 * NST + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
+  B.a_q = bars + 2 * NST + 2;         // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 6);
   float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
@@ -699,8 +707,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     }
     mbar_init(&B.acc_full[0], 1);
     mbar_init(&B.acc_full[1], 1);
-    mbar_init(B.a_lo, kEpiThreads);
-    mbar_init(B.a_hi, kEpiThreads);
+    for (int j = 0; j < 4; ++j) mbar_init(&B.a_q[j], kEpiThreads);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
@@ -765,13 +772,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               uint32_t a_idx = 0;  // A chunk of weight chunk kc = kc % a_chunks
               for (int kc = 0; kc < st.kchunks; ++kc) {
                 if (g == 0) {
-                  // the A image becomes available in two parts (hidden_step_staged)
-                  if (kc == 0) {
-                    ICLK(c_alo, mbar_wait(B.a_lo, par))
-                    if (st.k_lo == 0) ICLK(c_ahi, mbar_wait(B.a_hi, par))
-                    tc_fence_after();
-                  } else if (kc == st.k_lo) {
-                    ICLK(c_ahi, mbar_wait(B.a_hi, par))
+                  // the A image becomes available quarter by quarter (hidden_step_staged)
+                  if (st.k_lo == 0) {
+                    if (kc == 0) {
+                      ICLK(c_alo, for (int j = 0; j < 4; ++j) mbar_wait(&B.a_q[j], par))
+                      tc_fence_after();
+                    }
+                  } else if (kc < 4 * st.k_lo && kc % st.k_lo == 0) {
+                    ICLK(c_ahi, mbar_wait(&B.a_q[kc / st.k_lo], par))
                     tc_fence_after();
                   }
                 }
@@ -940,8 +948,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       fence_proxy_async_smem();
       if (p.steps[0].n_groups != 0) {
         tc_fence_before();
-        mbar_arrive(B.a_lo);
-        mbar_arrive(B.a_hi);
+        arrive_all_quarters(B);
       }
 
       for (int s = 0; s < p.n_steps; ++s) {
@@ -997,8 +1004,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             fence_proxy_async_smem();
             if (st.signal) {
               tc_fence_before();
-              mbar_arrive(B.a_lo);
-              mbar_arrive(B.a_hi);
+              arrive_all_quarters(B);
             }
           } break;
           case EPI_REV_HIDDEN: {
@@ -1076,8 +1082,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             fence_proxy_async_smem();
             if (st.signal) {
               tc_fence_before();
-              mbar_arrive(B.a_lo);
-              mbar_arrive(B.a_hi);
+              arrive_all_quarters(B);
             }
           } break;
           case EPI_ADJ_HIDDEN: {

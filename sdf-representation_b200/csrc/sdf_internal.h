@@ -46,9 +46,9 @@ struct StepDesc {
   int32_t k16;          // K=16 instructions per chunk
   uint32_t chunk_bytes;
   uint32_t w_off;       // byte offset of the first chunk of this step in the packed weight stream
-  int32_t k_lo;         // weight chunks of group 0 that only read A columns [0,256): they may start on the a_lo
-                        // barrier alone (0: the step needs the whole A image before its first MMA)
-  int32_t signal;       // 1: the A image this step leaves behind is consumed by a GEMM (arrive on a_lo / a_hi)
+  int32_t k_lo;         // weight chunks per 128-column quarter of a 512-wide A image: chunk kc of group 0 may start as
+                        // soon as quarter kc / k_lo is in place (0: the step needs the whole A image first)
+  int32_t signal;       // 1: the A image this step leaves behind is consumed by a GEMM (arrive on the a_q barriers)
 };
 
 // where the points of a tile come from
