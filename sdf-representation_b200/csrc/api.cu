@@ -11,9 +11,9 @@
 #include "sdf_internal.h"
 
 namespace sdf {
-cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int num_sms, cudaStream_t stream);
+cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int pair, int num_sms, cudaStream_t stream);
 cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
-                                int k16, int kind, float scale, int dtype, int split, cudaStream_t stream);
+                                int k16, int kind, float scale, int dtype, int split, int halves, cudaStream_t stream);
 cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream);
 cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
 cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
@@ -85,6 +85,7 @@ struct sdfnet_handle {
   sdfnet_desc d;
   int H, L, skip, num_sms;
   bool relu, parity;
+  bool pair;               // fast mode, H = 512: the chain kernel runs on CTA pairs (tcgen05 cta_group::2)
   int pts;                 // points per tile: 128 (fast) or 64 (parity)
   float* scale_dev = nullptr;      // [0] seed multiplier (power of two), [1] its inverse
   unsigned* absmax_dev = nullptr;  // running max |seed| of the current chunk
@@ -182,6 +183,9 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   h->relu = desc->beta == 0.f;
   h->parity = desc->precision == 1;
   h->pts = h->parity ? kParityPoints : kTileRows;
+  // CTA-pair layer chain (cta_group::2): functional and tested, but on B200 the cluster hand-shakes cost more than the
+  // halved weight traffic gains: opt-in with SDFNET_PAIR=1
+  h->pair = !h->parity && desc->hidden == 512 && getenv("SDFNET_PAIR") != nullptr;
   h->num_sms = prop.multiProcessorCount;
   const int H = h->H, L = h->L;
   uint32_t off = 0;
@@ -189,9 +193,9 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   h->R.resize(L);
   const bool sp = h->parity;
   h->F[0] = make_image(H, 1, 1, false, off);                  // K = 16 (input block, already split along K)
-  for (int l = 1; l < L; ++l) h->F[l] = make_image(H, H / 16, 4, sp, off);
+  for (int l = 1; l < L; ++l) h->F[l] = make_image(H, H / 16, h->pair ? 8 : 4, sp, off);
   h->F[L] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (row 0 = lin_L)
-  for (int l = L - 1; l >= 1; --l) h->R[l] = make_image(H, H / 16, 4, sp, off);
+  for (int l = L - 1; l >= 1; --l) h->R[l] = make_image(H, H / 16, h->pair ? 8 : 4, sp, off);
   h->R[0] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (rows 0..2 = d/dx)
   h->wpack_bytes = off;
   CU(cudaMalloc(&h->wpack, h->wpack_bytes));
@@ -266,14 +270,14 @@ extern "C" int sdfnet_pack_weights(sdfnet_t h, const float* const* W, const floa
     const int kind = l == 0 ? PK_F0 : (l == L ? PK_FL : PK_FH);
     const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
     CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           kind, scale, dt, s.split, stream));
+                           kind, scale, dt, s.split, h->pair ? 2 : 1, stream));
     CU(launch_pack_bias(b[l], out_dim_of(h, l), h->bias + static_cast<size_t>(l) * H, H, stream));
   }
   for (int l = L - 1; l >= 0; --l) {
     const StepImage& s = h->R[l];
     const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
     CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           l == 0 ? PK_R0 : PK_RH, scale, dt, s.split, stream));
+                           l == 0 ? PK_R0 : PK_RH, scale, dt, s.split, h->pair ? 2 : 1, stream));
   }
   CU(cudaMemcpyAsync(h->w_last, W[L], sizeof(float) * H, cudaMemcpyDeviceToDevice, stream));
   return 0;
@@ -340,7 +344,11 @@ size_t per_tile_bytes(const sdfnet_handle* h, int mode) {
   return 5 * h->L * ib + 3 * 2 * kGranuleBytes + kTileRows * 8 * sizeof(float);
 }
 // carve the workspace for `tiles` tiles
-void carve(const sdfnet_handle* h, int mode, uint8_t* ws, size_t tiles, Spill& s) {
+// images are laid out for an even number of tiles: the CTA-pair kernel walks tiles two at a time and its odd
+// partner of a ragged last pair works on a scratch tile
+static inline size_t even_tiles(size_t tiles) { return (tiles + 1) & ~static_cast<size_t>(1); }
+void carve(const sdfnet_handle* h, int mode, uint8_t* ws, size_t tiles_, Spill& s) {
+  const size_t tiles = even_tiles(tiles_);
   const size_t ib = img_bytes(h->H);
   const size_t arr = h->L * ib * tiles;
   memset(&s, 0, sizeof(s));
@@ -362,7 +370,7 @@ void carve(const sdfnet_handle* h, int mode, uint8_t* ws, size_t tiles, Spill& s
 
 extern "C" size_t sdfnet_workspace_bytes(sdfnet_t h, int64_t n_points, int32_t mode) {
   if (!h || n_points <= 0) return 0;
-  const size_t tiles = static_cast<size_t>((n_points + h->pts - 1) / h->pts);
+  const size_t tiles = (static_cast<size_t>((n_points + h->pts - 1) / h->pts) + 1) & ~static_cast<size_t>(1);
   return tiles * per_tile_bytes(h, mode) + 1024;
 }
 
@@ -380,10 +388,11 @@ static uint8_t* align_ws(void* ws, size_t& bytes) {
 static int run_forward(sdfnet_t h, ChainParams& p, int64_t n, cudaStream_t stream) {
   p.n = n;
   p.n_tiles = static_cast<int>((n + h->pts - 1) / h->pts);
+  p.tile_stride = (p.n_tiles + 1) & ~1;
   prog_forward(h, p);
   finish_program(p);
   Launch lr(h, PC_CHAIN_FG, stream);
-  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 
@@ -452,7 +461,7 @@ extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float*
   if (n <= 0) return 0;
   uint8_t* ws = align_ws(ws_, ws_bytes);
   const size_t ptb = per_tile_bytes(h, 0);
-  size_t cap_tiles = ws_bytes / ptb;
+  size_t cap_tiles = (ws_bytes / ptb) & ~static_cast<size_t>(1);
   if (!ws_ || cap_tiles == 0) return fail(1, "sdfnet_forward_grad: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, ptb);
   if (cap_tiles > (1u << 22)) cap_tiles = 1u << 22;
   const int64_t chunk = static_cast<int64_t>(cap_tiles) * h->pts;
@@ -466,6 +475,8 @@ extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float*
     p.g_out = grad_out + o * 3;
     p.n = m;
     p.n_tiles = static_cast<int>((m + h->pts - 1) / h->pts);
+  p.tile_stride = (p.n_tiles + 1) & ~1;
+    p.tile_stride = (p.n_tiles + 1) & ~1;
     Spill s;
     carve(h, 0, ws, p.n_tiles, s);
     p.Aimg = s.A;
@@ -474,7 +485,7 @@ extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float*
     prog_reverse(h, p);
     finish_program(p);
     Launch lr(h, PC_CHAIN_FG, static_cast<cudaStream_t>(stream));
-    CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, static_cast<cudaStream_t>(stream)));
+    CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, static_cast<cudaStream_t>(stream)));
   }
   return 0;
 }
@@ -501,7 +512,7 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   std::vector<DwItem> items;
   const int nmb = H / 128 > 0 ? H / 128 : 1;
   if (H % 128) return fail(1, "training requires hidden width multiple of 128 (got %d)", H);
-  const size_t arr = static_cast<size_t>(ib) * tiles;  // bytes of one layer of one spill array
+  const size_t arr = static_cast<size_t>(ib) * even_tiles(tiles);  // bytes of one layer of one spill array
   auto split_range = [&](int sp, int ksplit, uint32_t& t0, uint32_t& t1) {
     t0 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * sp / ksplit);
     t1 = static_cast<uint32_t>(static_cast<int64_t>(tiles) * (sp + 1) / ksplit);
@@ -610,6 +621,7 @@ int run_fg(sdfnet_t h, const float* x, int64_t m, const Spill& s, bool need_g, c
   p.x = x;
   p.n = m;
   p.n_tiles = static_cast<int>((m + h->pts - 1) / h->pts);
+  p.tile_stride = (p.n_tiles + 1) & ~1;
   p.f_out = s.f;
   p.g_out = need_g ? s.g : nullptr;
   p.Aimg = s.A; p.Qimg = s.Q; p.Ximg = s.X;
@@ -618,7 +630,7 @@ int run_fg(sdfnet_t h, const float* x, int64_t m, const Spill& s, bool need_g, c
   if (need_g) prog_reverse(h, p);
   finish_program(p);
   Launch lr(h, PC_CHAIN_FG, stream);
-  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 // tangent (+adjoint) sweeps over one chunk
@@ -627,6 +639,7 @@ int run_ta(sdfnet_t h, int64_t m, const Spill& s, const float* fbar, const float
   base_params(h, p);
   p.n = m;
   p.n_tiles = static_cast<int>((m + h->pts - 1) / h->pts);
+  p.tile_stride = (p.n_tiles + 1) & ~1;
   p.fbar = fbar; p.gbar = gbar; p.seed_mult = h->scale_dev;
   p.Aimg = s.A; p.Qimg = s.Q; p.ADimg = s.AD; p.Uimg = s.U; p.Zimg = s.Z; p.Ximg = s.X; p.Gimg = s.G; p.Simg = s.S;
   if (gbar) {
@@ -636,11 +649,11 @@ int run_ta(sdfnet_t h, int64_t m, const Spill& s, const float* fbar, const float
   prog_adjoint(h, p);
   finish_program(p);
   Launch lr(h, PC_CHAIN_TA, stream);
-  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 int64_t chunk_points(sdfnet_t h, size_t ws_bytes) {
-  size_t cap_tiles = ws_bytes / per_tile_bytes(h, 1);
+  size_t cap_tiles = (ws_bytes / per_tile_bytes(h, 1)) & ~static_cast<size_t>(1);
   if (cap_tiles > (1u << 22)) cap_tiles = 1u << 22;
   return static_cast<int64_t>(cap_tiles) * h->pts;
 }

@@ -22,24 +22,28 @@ __device__ __forceinline__ uint16_t bits16(float v, int dtype) {
 
 // ------------------------------------------------------------------------------------------------
 // Weight packing.  One launch per step image.  Destination element order (see chain.cu MMA loop):
-//   [group g][k-chunk kc][granule gr (2*k16 per chunk)][row (ng)][8 elements]
-// logical operand B[n][k] with n = g*ng + row, k = (kc*2*k16 + gr)*8 + e.
+//   [group g][k-chunk kc][half hf (halves)][granule gr (2*k16 per chunk)][row (ng / halves)][8 elements]
+// logical operand B[n][k] with n = g*ng + hf*(ng/halves) + row, k = (kc*2*k16 + gr)*8 + e.
+// halves = 2 is the CTA-pair layout: CTA r of a pair streams the contiguous half hf = r of every chunk.
 // ------------------------------------------------------------------------------------------------
 enum : int { PK_F0 = 0, PK_FH = 1, PK_FL = 2, PK_RH = 3, PK_R0 = 4 };
 
 // split != 0 (parity mode): kchunks counts hi chunks followed by lo chunks, lo = rnd16(v - rnd16(v)).
 __global__ void pack_weights_kernel(const float* __restrict__ W, int out_dim, int in_dim, uint16_t* __restrict__ dst,
-                                    int n_groups, int ng, int kchunks, int k16, int kind, float scale, int dtype, int split) {
+                                    int n_groups, int ng, int kchunks, int k16, int kind, float scale, int dtype, int split,
+                                    int halves) {
   const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
+  const int hrows = ng / halves;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
     long t = idx;
     const int e = static_cast<int>(t % 8); t /= 8;
-    const int row = static_cast<int>(t % ng); t /= ng;
+    const int row = static_cast<int>(t % hrows); t /= hrows;
     const int gr = static_cast<int>(t % (2 * k16)); t /= (2 * k16);
+    const int hf = static_cast<int>(t % halves); t /= halves;
     int kc = static_cast<int>(t % kchunks); t /= kchunks;
     const int g = static_cast<int>(t);
-    const int n = g * ng + row;
+    const int n = g * ng + hf * hrows + row;
     bool lo_part = false;
     if (split) {
       lo_part = kc >= kchunks / 2;
@@ -78,13 +82,13 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, int out_dim, float
 }
 
 cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
-                                int k16, int kind, float scale, int dtype, int split, cudaStream_t stream) {
+                                int k16, int kind, float scale, int dtype, int split, int halves, cudaStream_t stream) {
   const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
   if (blocks < 1) blocks = 1;
   pack_weights_kernel<<<blocks, 256, 0, stream>>>(W, out_dim, in_dim, static_cast<uint16_t*>(dst), n_groups, ng, kchunks,
-                                                  k16, kind, scale, dtype, split);
+                                                  k16, kind, scale, dtype, split, halves);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream) {

@@ -59,12 +59,17 @@ constexpr int kChainThreads = kEpiThreads + 128;
 constexpr uint32_t kABytes = kMaxH / 8 * kGranuleBytes;  // 131072
 constexpr uint32_t kScratchBytes = 4 * 32 * kParityPoints * 4;  // parity: lane-half exchange, [h][32 cols][64 points] fp32
 
-template <bool PAR>
+// PAIR: the kernel runs on CTA pairs (cluster of 2, tcgen05 cta_group::2).  Each CTA keeps its own 128-point tile, A
+// image, accumulators and epilogue; the leader CTA issues M = 256 MMAs over both tiles, and each CTA streams only its
+// half (N / 2 rows) of every weight chunk: half the L2 -> SM weight bytes and half the shared-memory operand traffic
+// per FLOP; the ring stages keep their 32 KB (bulk copies have a large fixed cost) and hold half chunks of twice the K.
+template <bool PAR, bool PAIR = false>
 struct ChainCfg {
   static constexpr int kStages = PAR ? 2 : 3;
+  static constexpr uint32_t kStage = kStageBytes;  // bytes of one ring stage (pair: half of a K = 128 chunk)
   static constexpr int kPoints = PAR ? kParityPoints : kTileRows;
-  static constexpr uint32_t kBarOff = kABytes + kStages * kStageBytes;
-  static constexpr uint32_t kGskipOff = kBarOff + 128;
+  static constexpr uint32_t kBarOff = kABytes + kStages * kStage;
+  static constexpr uint32_t kGskipOff = kBarOff + 256;
   static constexpr uint32_t kScratchOff = kGskipOff + kTileRows * 3 * 4;
   static constexpr uint32_t kSmem = kScratchOff + (PAR ? kScratchBytes : 0);
 };
@@ -225,10 +230,25 @@ __device__ __forceinline__ void put_block(const Epi& e, int g, const uint4& v, b
 struct Bars {
   uint64_t* acc_full;  // [2]  MMA issuer -> epilogue: accumulator half g is complete
   uint64_t* a_q;       // [4]  epilogue -> MMA issuer: A-image columns [128 j, 128 j + 128) are in place
+  bool remote;         //      CTA pair, rank 1: the issuer's barriers live in the leader CTA
 };
+// One arrival per epilogue warp on quarter barrier j (every lane has fenced its own shared-memory / TMEM accesses).
+__device__ __forceinline__ void arrive_quarter(const Bars& B, int j) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    if (B.remote) mbar_arrive_cluster(&B.a_q[j], 0);
+    else mbar_arrive(&B.a_q[j]);
+  }
+}
 __device__ __forceinline__ void arrive_all_quarters(const Bars& B) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) mbar_arrive(&B.a_q[j]);
+    for (int j = 0; j < 4; ++j) {
+      if (B.remote) mbar_arrive_cluster(&B.a_q[j], 0);
+      else mbar_arrive(&B.a_q[j]);
+    }
+  }
 }
 
 struct EpiConst {
@@ -602,8 +622,8 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       fence_proxy_async_smem();
       if (st.signal) {
         tc_fence_before();
-        mbar_arrive(&B.a_q[0]);
-        mbar_arrive(&B.a_q[1]);
+        arrive_quarter(B, 0);
+        arrive_quarter(B, 1);
       }
       CLK_MARK(EPI, 3);
     }
@@ -655,7 +675,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
         if (pc == 1) {
           // this thread's share of A columns [256,384) is written: the next GEMM may run two more weight chunks
           fence_proxy_async_smem();
-          if (st.signal) mbar_arrive(&B.a_q[2]);
+          if (st.signal) arrive_quarter(B, 2);
         }
       }
     }
@@ -663,7 +683,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
   fence_proxy_async_smem();
   if (st.signal) {
     tc_fence_before();
-    mbar_arrive(&B.a_q[3]);
+    arrive_quarter(B, 3);
   }
   CLK_MARK(EPI, 4);
 #ifdef SDF_CLOCKS
@@ -680,39 +700,59 @@ __device__ __forceinline__ void hidden_step(Epi& e, const StepIO& io, const EpiC
   if (st.n_groups == 2) ++n1;
 }
 
-template <int DT, bool PAR>
+template <bool PAIR>
+__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (PAIR) umma_f16_ss2(tmem_d, da, db, idesc, accumulate);
+  else umma_f16_ss(tmem_d, da, db, idesc, accumulate);
+}
+
+template <int DT, bool PAR, bool PAIR>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
-  using Cfg = ChainCfg<PAR>;
+  using Cfg = ChainCfg<PAR, PAIR>;
   constexpr int NST = Cfg::kStages;
   constexpr int PTS = Cfg::kPoints;
+  constexpr uint32_t kStage = Cfg::kStage;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
-  uint64_t* w_full = bars;            // [NST]
-  uint64_t* w_empty = bars + NST;     // [NST]
+  uint64_t* w_full = bars;                // [NST] this CTA's (half) chunk has landed
+  uint64_t* w_empty = bars + NST;         // [NST] the MMAs reading the stage are done (pair: signalled in both CTAs)
+  uint64_t* peer_full = bars + 2 * NST;   // [NST] pair, leader only: the peer's half chunk has landed
   Bars B;
-  B.acc_full = bars + 2 * NST;        // [2]
-  B.a_q = bars + 2 * NST + 2;         // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 6);
+  B.acc_full = bars + 3 * NST;            // [2]
+  B.a_q = bars + 3 * NST + 2;             // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 6);
   float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  B.remote = PAIR && rank != 0;
+  // tiles are walked two at a time by a pair: pair i works on tiles 2i (leader) and 2i + 1 (peer); the peer of a
+  // ragged last pair works on the scratch tile n_tiles (all rows invalid, images inside the even-padded arrays)
+  const int it0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int it_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int it_end = PAIR ? (p.n_tiles + 1) / 2 : p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
+      mbar_init(&peer_full[i], 1);
     }
     mbar_init(&B.acc_full[0], 1);
     mbar_init(&B.acc_full[1], 1);
-    for (int j = 0; j < 4; ++j) mbar_init(&B.a_q[j], kEpiThreads);
+    for (int j = 0; j < 4; ++j) mbar_init(&B.a_q[j], kEpiWarps * (PAIR ? 2 : 1));
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) {
+    if (PAIR) tmem_alloc2<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // barrier inits and the TMEM allocations of both CTAs are in place
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t ib = img_bytes(p.H);
@@ -724,7 +764,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       // ------------------------------------------------------------------ weight producer
       if (lane == 0) {
         uint32_t stage = 0, round = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int it = it0; it < it_end; it += it_step) {
+          const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
+          (void)tile;
           for (int s = 0; s < p.n_steps; ++s) {
             const StepDesc& st = p.steps[s];
             const int nchunks = st.n_groups * st.kchunks;
@@ -737,17 +779,33 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               } else
 #endif
               {
-                mbar_arrive_expect_tx(&w_full[stage], st.chunk_bytes);
-                bulk_g2s(sW + stage * kStageBytes, src + static_cast<size_t>(c) * st.chunk_bytes, st.chunk_bytes,
-                         &w_full[stage]);
+                const uint32_t bytes = PAIR ? st.chunk_bytes / 2 : st.chunk_bytes;
+                mbar_arrive_expect_tx(&w_full[stage], bytes);
+                bulk_g2s(sW + stage * kStage, src + static_cast<size_t>(c) * st.chunk_bytes + rank * bytes, bytes, &w_full[stage]);
               }
               if (++stage == NST) { stage = 0; ++round; }
             }
           }
         }
       }
+    } else if (warp == kMmaWarp && PAIR && rank != 0) {
+      // ------------------------------------------------------------------ peer CTA: tell the leader when this CTA's
+      // half of a weight chunk is in shared memory
+      if (lane == 0) {
+        uint32_t stage = 0, round = 0;
+        for (int it = it0; it < it_end; it += it_step) {
+          for (int s = 0; s < p.n_steps; ++s) {
+            const int nchunks = p.steps[s].n_groups * p.steps[s].kchunks;
+            for (int c = 0; c < nchunks; ++c) {
+              mbar_wait(&w_full[stage], round & 1);
+              mbar_arrive_cluster(&peer_full[stage], 0);
+              if (++stage == NST) { stage = 0; ++round; }
+            }
+          }
+        }
+      }
     } else if (warp == kMmaWarp) {
-      // ------------------------------------------------------------------ MMA issuer
+      // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
       if (lane == 0) {
         uint32_t stage = 0, round = 0, n0 = 0;
         const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
@@ -758,13 +816,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 #else
 #define ICLK(var, stmt) stmt;
 #endif
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int it = it0; it < it_end; it += it_step) {
+          const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
+          (void)tile;
           for (int s = 0; s < p.n_steps; ++s) {
             const StepDesc& st = p.steps[s];
             if (st.n_groups == 0) continue;
             const uint32_t par = n0 & 1;
-            const uint32_t idesc = make_idesc_f16(kTileRows, st.ng, DT == DT_BF16, false, false);
-            const uint32_t b_lbo = static_cast<uint32_t>(st.ng) * 16;
+            const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTileRows : kTileRows, st.ng, DT == DT_BF16, false, false);
+            const uint32_t b_lbo = static_cast<uint32_t>(PAIR ? st.ng / 2 : st.ng) * 16;  // rows of B in this CTA x 16 B
             const uint64_t db_step = (2 * b_lbo) >> 4;
             const uint32_t a_chunk_bytes = static_cast<uint32_t>(st.k16 * 2) * kGranuleBytes;
             for (int g = 0; g < st.n_groups; ++g) {
@@ -775,40 +835,40 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                   // the A image becomes available quarter by quarter (hidden_step_staged)
                   if (st.k_lo == 0) {
                     if (kc == 0) {
-                      ICLK(c_alo, for (int j = 0; j < 4; ++j) mbar_wait(&B.a_q[j], par))
+                      ICLK(c_alo, for (int j = 0; j < 4; ++j) { if (PAIR) mbar_wait_cluster(&B.a_q[j], par); else mbar_wait(&B.a_q[j], par); })
                       tc_fence_after();
                     }
                   } else if (kc < 4 * st.k_lo && kc % st.k_lo == 0) {
-                    ICLK(c_ahi, mbar_wait(&B.a_q[kc / st.k_lo], par))
+                    ICLK(c_ahi, if (PAIR) mbar_wait_cluster(&B.a_q[kc / st.k_lo], par); else mbar_wait(&B.a_q[kc / st.k_lo], par))
                     tc_fence_after();
                   }
                 }
-                ICLK(c_w, mbar_wait(&w_full[stage], round & 1))
+                ICLK(c_w, mbar_wait(&w_full[stage], round & 1); if (PAIR) mbar_wait_cluster(&peer_full[stage], round & 1))
                 tc_fence_after();
                 // descriptors of the chunk's first K=16 slice; the following slices only advance the 14-bit start
                 // address fields (shared memory addresses stay below 2^18, so the adds never carry out of the field)
                 const uint64_t da0 = make_smem_desc(sA_u + a_idx * a_chunk_bytes, kGranuleBytes, 128);
-                const uint64_t db0 = make_smem_desc(sW_u + stage * kStageBytes, b_lbo, 128);
+                const uint64_t db0 = make_smem_desc(sW_u + stage * kStage, b_lbo, 128);
                 if (++a_idx == static_cast<uint32_t>(st.a_chunks)) a_idx = 0;
 #ifdef SDF_CLOCKS
                 if (!(p.flags & FL_DBG_NO_MMA))
 #endif
                 {
-                  if (st.k16 == 4) {
+                  if (st.k16 == (PAIR ? 8 : 4)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      umma_f16_ss(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
-                                  (kc | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < (PAIR ? 8 : 4); ++k)
+                      umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                     (kc | k) != 0 ? 1u : 0u);
                   } else {
                     for (int k = 0; k < st.k16; ++k)
-                      umma_f16_ss(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
-                                  (kc | k) != 0 ? 1u : 0u);
+                      umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                     (kc | k) != 0 ? 1u : 0u);
                   }
                 }
-                umma_commit(&w_empty[stage]);
+                if (PAIR) umma_commit2(&w_empty[stage], 3); else umma_commit(&w_empty[stage]);
                 if (++stage == NST) { stage = 0; ++round; }
               }
-              umma_commit(&B.acc_full[g]);
+              if (PAIR) umma_commit2(&B.acc_full[g], 3); else umma_commit(&B.acc_full[g]);
             }
             ++n0;
 #ifdef SDF_CLOCKS
@@ -876,7 +936,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     const int inj_layer = p.skip > 0 ? p.skip - 1 : -1;
     const bool has_u = (p.flags & FL_TANGENT) && !relu;
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int it = it0; it < it_end; it += it_step) {
+          const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
+          (void)tile;
       e.grow = static_cast<int64_t>(tile) * PTS + e.prow;
       e.valid = e.grow < p.n;
       // ---------------------------------------------------------------- prologue: input block (column groups 0, 1
@@ -961,7 +1023,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         io.special = false;
         switch (st.epi) {
           case EPI_FWD_HIDDEN: {
-            io.out = ((p.flags & FL_SPILL_A) && !no_stg) ? img_ptr(p.Aimg, l, p.n_tiles, tile, ib) : nullptr;
+            io.out = ((p.flags & FL_SPILL_A) && !no_stg) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
             io.vec = p.bias + l * p.H;
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_FWD_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
@@ -983,7 +1045,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           } break;
           case EPI_REV_START: {
             // q_{L-1} = w_L * act'(z_{L-1}); the A image still holds a_{L-1}
-            uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l, p.n_tiles, tile, ib) : nullptr;
+            uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l, p.tile_stride, tile, ib) : nullptr;
             if (e.math) {
               for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
 #pragma unroll
@@ -1009,8 +1071,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           } break;
           case EPI_REV_HIDDEN: {
             // GEMM r = q_l W_l done; q_{l-1} = r * act'(z_{l-1});  l = st.layer
-            io.in_a = img_ptr(p.Aimg, l - 1, p.n_tiles, tile, ib);
-            io.out = ((p.flags & FL_SPILL_Q) && !no_stg) ? img_ptr(p.Qimg, l - 1, p.n_tiles, tile, ib) : nullptr;
+            io.in_a = img_ptr(p.Aimg, l - 1, p.tile_stride, tile, ib);
+            io.out = ((p.flags & FL_SPILL_Q) && !no_stg) ? img_ptr(p.Qimg, l - 1, p.tile_stride, tile, ib) : nullptr;
             io.special = (l - 1) == inj_layer;
             hidden_step<DT, PAR, EPI_REV_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
@@ -1039,18 +1101,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             named_bar_sync(1, kEpiThreads);  // gskip may be rewritten by the next tile
           } break;
           case EPI_TAN_HIDDEN: {
-            io.in_a = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
-            io.in_b = relu ? nullptr : img_ptr(p.Qimg, l, p.n_tiles, tile, ib);
-            io.out = no_stg ? nullptr : img_ptr(p.ADimg, l, p.n_tiles, tile, ib);
-            io.out_u = relu ? nullptr : img_ptr(p.Uimg, l, p.n_tiles, tile, ib);
+            io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
+            io.in_b = relu ? nullptr : img_ptr(p.Qimg, l, p.tile_stride, tile, ib);
+            io.out = no_stg ? nullptr : img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
+            io.out_u = relu ? nullptr : img_ptr(p.Uimg, l, p.tile_stride, tile, ib);
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_TAN_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           case EPI_ADJ_START: {
             // Zbar_{L-1} = s' * (w_L fbar) + u_{L-1}
-            const uint8_t* aimg = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
-            const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
-            uint8_t* zimg = img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
+            const uint8_t* aimg = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
+            const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.tile_stride, tile, ib) : nullptr;
+            uint8_t* zimg = img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
             if (e.math) {
               for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
 #pragma unroll
@@ -1086,9 +1148,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             }
           } break;
           case EPI_ADJ_HIDDEN: {
-            io.in_a = img_ptr(p.Aimg, l, p.n_tiles, tile, ib);
-            io.in_b = has_u ? img_ptr(p.Uimg, l, p.n_tiles, tile, ib) : nullptr;
-            io.out = no_stg ? nullptr : img_ptr(p.Zimg, l, p.n_tiles, tile, ib);
+            io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
+            io.in_b = has_u ? img_ptr(p.Uimg, l, p.tile_stride, tile, ib) : nullptr;
+            io.out = no_stg ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_ADJ_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
@@ -1103,31 +1165,53 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+  if (PAIR) cluster_sync_all();  // the peer's shared memory and TMEM stay valid until both CTAs are done
+  else __syncthreads();
+  if (warp == kMmaWarp) {
+    if (PAIR) tmem_dealloc2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int DT, bool PAR>
+template <int DT, bool PAR, bool PAIR>
 static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kfn = chain_kernel<DT, PAR>;
-  constexpr uint32_t smem = ChainCfg<PAR>::kSmem;
+  auto kfn = chain_kernel<DT, PAR, PAIR>;
+  constexpr uint32_t smem = ChainCfg<PAR, PAIR>::kSmem;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    const int pairs_needed = (p.n_tiles + 1) / 2;
+    const int pairs = pairs_needed < num_sms / 2 ? pairs_needed : num_sms / 2;
+    cfg.gridDim = dim3(2 * pairs);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(p.n_tiles < num_sms ? p.n_tiles : num_sms);
+  }
+  cfg.blockDim = dim3(kChainThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
 #ifdef SDF_CLOCKS
   {
     // measurement build: synchronous launch, per-kind cycle report of epilogue thread 0 (averaged over CTAs and steps)
+    const int grid = static_cast<int>(cfg.gridDim.x);
     ChainParams q = p;
     cudaMalloc(&q.dbg_clk, sizeof(long long) * 72);
     cudaMemsetAsync(q.dbg_clk, 0, sizeof(long long) * 72, stream);
-    kfn<<<grid, kChainThreads, smem, stream>>>(q);
+    cudaLaunchKernelEx(&cfg, kfn, q);
     cudaStreamSynchronize(stream);
     long long hb[72];
     cudaMemcpy(hb, q.dbg_clk, sizeof(hb), cudaMemcpyDeviceToHost);
@@ -1146,14 +1230,15 @@ static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t st
     return cudaGetLastError();
   }
 #endif
-  kfn<<<grid, kChainThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, p);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int num_sms, cudaStream_t stream) {
+cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int pair, int num_sms, cudaStream_t stream) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  if (dtype == DT_BF16) return parity ? launch_one<DT_BF16, true>(p, num_sms, stream) : launch_one<DT_BF16, false>(p, num_sms, stream);
-  return parity ? launch_one<DT_FP16, true>(p, num_sms, stream) : launch_one<DT_FP16, false>(p, num_sms, stream);
+  if (parity) return dtype == DT_BF16 ? launch_one<DT_BF16, true, false>(p, num_sms, stream) : launch_one<DT_FP16, true, false>(p, num_sms, stream);
+  if (pair) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true>(p, num_sms, stream) : launch_one<DT_FP16, false, true>(p, num_sms, stream);
+  return dtype == DT_BF16 ? launch_one<DT_BF16, false, false>(p, num_sms, stream) : launch_one<DT_FP16, false, false>(p, num_sms, stream);
 }
 
 }  // namespace sdf

@@ -81,6 +81,7 @@ struct ChainParams {
   // points
   int64_t n;               // valid points
   int32_t n_tiles;
+  int32_t tile_stride;     // tiles per layer in the spill arrays (n_tiles rounded up to even)
   int32_t src;
   const float* x;          // SRC_POINTS: [n][3]
   const float* axis;       // SRC_GRID: [grid_n] axis vector (torch.linspace output)

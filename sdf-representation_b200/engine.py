@@ -122,7 +122,7 @@ class Engine:
     def workspace(self, n_points, mode):
         need = int(self.lib.sdfnet_workspace_bytes(self.handle, int(n_points), int(mode)))
         need = min(need, _WS_CAP_BYTES)
-        per_tile = int(self.lib.sdfnet_workspace_bytes(self.handle, 128, int(mode)))
+        per_tile = int(self.lib.sdfnet_workspace_bytes(self.handle, 256, int(mode)))  # 256 points = an even tile count
         need = max(need, per_tile + 4096)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
@@ -130,9 +130,8 @@ class Engine:
         return self._ws
 
     def _chunks(self, n, mode):
-        per_tile = int(self.lib.sdfnet_workspace_bytes(self.handle, 128, int(mode))) - 1024
-        cap_tiles = max(1, (self._ws.numel() - 1024) // per_tile)
-        pts = cap_tiles * 128
+        per_256 = int(self.lib.sdfnet_workspace_bytes(self.handle, 256, int(mode))) - 1024
+        pts = max(1, (self._ws.numel() - 1024) // per_256) * 256
         return max(1, math.ceil(n / pts))
 
     # ------------------------------------------------------------------ inference
