@@ -541,6 +541,11 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
             d.b_off = static_cast<uint32_t>(nh) * 32 * kGranuleBytes;
             d.n = 256; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1;
             d.out = gl.main_acc + (static_cast<size_t>(l - 1) * H + static_cast<size_t>(nh) * 256) * H + mb * 256;
+            // Zbar_l^T . Xblock (bias gradients, column 15) rides along with the Zbar_l tiles.  Every block of the
+            // layer does the (cheap, N = 16) product so that the pairs sharing operand tiles stay in step -- which is
+            // what lets L2 serve their second reads -- but only the nh == 0 blocks add it to the result.
+            d.X = s.X; d.x_tstride = xb;
+            d.out_x = nh == 0 ? gl.zx_acc + static_cast<size_t>(l) * 16 * H + mb * 256 : nullptr;
             items.push_back(d);
           }
     }
@@ -548,7 +553,7 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   }
   const int nb = H > 256 ? 256 : H;       // N per main item
   const int nnh = H / nb;
-  const int types = (use_pairs ? 0 : (L - 1) * nmb * nnh) + (L + 3) * nmb;
+  const int types = (use_pairs ? 0 : (L - 1) * nmb * nnh) + ((use_pairs ? 1 : L) + 3) * nmb;
   int ksplit = (8 * h->num_sms + types - 1) / types;
   if (ksplit > tiles) ksplit = tiles;
   if (ksplit < 1) ksplit = 1;
@@ -572,7 +577,8 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
     }
     for (int mb = 0; mb < nmb; ++mb) {
       const uint32_t aoff = static_cast<uint32_t>(mb) * 16 * kGranuleBytes;
-      for (int l = 0; l < L; ++l) {   // Zbar_l^T . Xblock -> biases (col 15) and, for l = 0, dW_0 term 1
+      for (int l = 0; l < (use_pairs ? 1 : L); ++l) {   // Zbar_l^T . Xblock -> biases (col 15) and, for l = 0, dW_0 term 1
+        // (with the CTA-pair kernel the layers l >= 1 are folded into its items)
         DwItem d{};
         d.A1 = s.Z + arr * l; d.B1 = s.X; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
         d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1;

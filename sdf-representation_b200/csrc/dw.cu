@@ -169,7 +169,8 @@ cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parit
 // ------------------------------------------------------------------------------------------------
 constexpr int kDw2Stages = 3;
 constexpr uint32_t kDw2Half = 16 * kGranuleBytes;        // 128 features x 128 points
-constexpr uint32_t kDw2StageBytes = 2 * kDw2Half;        // A half + B half
+constexpr uint32_t kDw2XBytes = kGranuleBytes;            // this CTA's 8 columns of a 16-column block image
+constexpr uint32_t kDw2StageBytes = 2 * kDw2Half + kDw2XBytes;  // A half + B half + block-image granule
 constexpr uint32_t kDw2Smem = kDw2Stages * kDw2StageBytes + 256;
 
 template <int DT>
@@ -215,11 +216,13 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
           for (int term = 0; term < nterms; ++term) {
             const uint8_t* a = (term ? d.A2 : d.A1) + static_cast<size_t>(tile) * d.a_tstride + d.a_off + rank * kDw2Half;
             const uint8_t* b = (term ? d.B2 : d.B1) + static_cast<size_t>(tile) * d.b_tstride + d.b_off + rank * kDw2Half;
+            const bool with_x = d.X != nullptr && term == 0;
             mbar_wait(&empty[stage], (round & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[stage], kDw2StageBytes);
+            mbar_arrive_expect_tx(&full[stage], 2 * kDw2Half + (with_x ? kDw2XBytes : 0u));
             uint8_t* dst = smem + stage * kDw2StageBytes;
             bulk_g2s(dst, a, kDw2Half, &full[stage]);
             bulk_g2s(dst + kDw2Half, b, kDw2Half, &full[stage]);
+            if (with_x) bulk_g2s(dst + 2 * kDw2Half, d.X + static_cast<size_t>(tile) * d.x_tstride + rank * kDw2XBytes, kDw2XBytes, &full[stage]);
             if (++stage == kDw2Stages) { stage = 0; ++round; }
           }
         }
@@ -243,13 +246,21 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
         const uint32_t lbo = 128u;            // K-group (8 image rows) stride
         const uint32_t sbo = kGranuleBytes;   // MN-block (8 features) stride
         const uint32_t idesc = make_idesc_f16(256, 256, DT == DT_BF16, true, true);
+        const uint32_t idesc_x = make_idesc_f16(256, 16, DT == DT_BF16, true, true);
+        uint32_t uses[2] = {0, 0};  // acquisitions of each accumulator slot so far (barrier phases)
         for (int it = pair; it < n_items; it += n_pairs, ++item_cnt) {
           const DwItem d = items[it];
           const uint32_t as = item_cnt & 1;
-          mbar_wait_cluster(&acc_empty[as], ((item_cnt >> 1) & 1) ^ 1);
+          // an item with a block-image product keeps its 16 extra columns in the other slot: it owns both
+          mbar_wait_cluster(&acc_empty[as], (uses[as] & 1) ^ 1);
+          ++uses[as];
+          if (d.X) {
+            mbar_wait_cluster(&acc_empty[as ^ 1], (uses[as ^ 1] & 1) ^ 1);
+            ++uses[as ^ 1];
+          }
           tc_fence_after();
           const int nterms = d.A2 ? 2 : 1;
-          uint32_t first = 1;
+          uint32_t first = 1, first_x = 1;
           for (uint32_t tile = d.tile0; tile < d.tile1; ++tile) {
             for (int term = 0; term < nterms; ++term) {
               mbar_wait(&full[stage], round & 1);
@@ -278,22 +289,50 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
                   }
                 }
               }
+              if (d.X && term == 0) {
+                const uint64_t dx0 = make_smem_desc(b_addr + kDw2Half, lbo, sbo);
+                const uint32_t tx = tmem_base + (as ^ 1) * 256;
+                if (!parity) {
+#pragma unroll
+                  for (int k = 0; k < kTileRows / 16; ++k) {
+                    umma_f16_ss2(tx, da0 + static_cast<uint64_t>(k) * 16, dx0 + static_cast<uint64_t>(k) * 16, idesc_x, first_x ? 0u : 1u);
+                    first_x = 0;
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < kParityPoints / 16; ++k) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                      const uint32_t ka = k + (c == 1 ? 4 : 0), kb = k + (c == 2 ? 4 : 0);
+                      umma_f16_ss2(tx, da0 + static_cast<uint64_t>(ka) * 16, dx0 + static_cast<uint64_t>(kb) * 16, idesc_x, first_x ? 0u : 1u);
+                      first_x = 0;
+                    }
+                  }
+                }
+              }
               umma_commit2(&empty[stage], 3);
               if (++stage == kDw2Stages) { stage = 0; ++round; }
             }
           }
           umma_commit2(&acc_full[as], 3);
+          if (d.X) umma_commit2(&acc_full[as ^ 1], 3);
         }
       }
     }
   } else {
     uint32_t item_cnt = 0;
+    uint32_t uses[2] = {0, 0};
     const int m = static_cast<int>(rank) * 128 + warp * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     for (int it = pair; it < n_items; it += n_pairs, ++item_cnt) {
       const DwItem d = items[it];
       const uint32_t as = item_cnt & 1;
-      mbar_wait(&acc_full[as], (item_cnt >> 1) & 1);
+      mbar_wait(&acc_full[as], uses[as] & 1);
+      ++uses[as];
+      if (d.X) {
+        mbar_wait(&acc_full[as ^ 1], uses[as ^ 1] & 1);
+        ++uses[as ^ 1];
+      }
       tc_fence_after();
       if (d.tile1 > d.tile0) {
         const float im = d.inv_mult ? __ldg(d.inv_mult) : 1.f;
@@ -304,10 +343,21 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) atomicAdd(d.out + static_cast<size_t>(c0 + j) * d.out_ld + m, __uint_as_float(r[j]) * im);
         }
+        if (d.out_x) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + (as ^ 1) * 256, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(d.out_x + static_cast<size_t>(j) * d.out_ld + m, __uint_as_float(r[j]) * im);
+        }
       }
       tc_fence_before();
       if (rank == 0) mbar_arrive(&acc_empty[as]);
       else mbar_arrive_cluster(&acc_empty[as], 0);
+      if (d.X) {
+        if (rank == 0) mbar_arrive(&acc_empty[as ^ 1]);
+        else mbar_arrive_cluster(&acc_empty[as ^ 1], 0);
+      }
     }
   }
   tc_fence_before();

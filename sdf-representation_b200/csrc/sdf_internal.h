@@ -125,6 +125,11 @@ struct DwItem {
   uint32_t out_ld;                 // leading dimension (elements) of out (index [n][m])
   float* out;
   const float* inv_mult;           // device scalar multiplied into the result (nullptr = 1)
+  // CTA-pair kernel only: the first term's A operand is also multiplied with a 16-column block image (bias / first
+  // layer products ride along with the tile that is in shared memory anyway): out_x[16][m] += A1^T X
+  const uint8_t* X;                // nullptr: none
+  uint32_t x_tstride;
+  float* out_x;
 };
 
 __host__ __device__ inline uint32_t img_bytes(int H) { return static_cast<uint32_t>(H / 8) * kGranuleBytes; }
