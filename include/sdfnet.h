@@ -111,6 +111,9 @@ int sdfnet_adam_step(float* params, const float* grads, float* exp_avg, float* e
  * list of active cells (mask not 0 or 255). */
 int sdfnet_mc_classify(const float* sdf, int32_t nx, int32_t ny, int32_t nz, uint8_t* case_index,
                        int64_t* active_cells, int64_t* n_active, void* stream);
+/* Second phase on its own: active_cells == NULL only counts the active cells into *n_active (so the caller can size
+ * the index buffer exactly), otherwise writes their flat indices in ascending order. */
+int sdfnet_mc_compact(const uint8_t* case_index, int64_t n_cells, int64_t* active_cells, int64_t* n_active, void* stream);
 
 /* Instrumentation (no reference counterpart; used by bench.py): kernels launched through this handle so far, and
  * CUDA-event timing of each kernel class on its launch stream.  Classes: 0 = layer chain forward (+ reverse),

@@ -37,6 +37,7 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n,
 cudaError_t launch_octree_flags(const float* sdf, int64_t n, float thresh, uint8_t* flags, cudaStream_t stream);
 cudaError_t launch_mc_classify(const float* sdf, int nx, int ny, int nz, uint8_t* cases, cudaStream_t stream);
 long compact_num_blocks(long n);
+cudaError_t launch_count_flags(const uint8_t* v, long n, int mode, long* total, long* scratch, cudaStream_t stream);
 cudaError_t launch_compact(const uint8_t* v, long n, int mode, const uint64_t* keys, long* out_idx, uint64_t* out_keys,
                            long* total, long* scratch, cudaStream_t stream);
 }  // namespace sdf
@@ -828,18 +829,30 @@ extern "C" int sdfnet_mc_classify(const float* sdf, int32_t nx, int32_t ny, int3
                                   int64_t* active_cells, int64_t* n_active, void* stream_) {
   if (!sdf || !case_index) return fail(1, "sdfnet_mc_classify: null argument");
   if (nx < 2 || ny < 2 || nz < 2) return fail(1, "sdfnet_mc_classify: block must be at least 2x2x2");
+  if (nx > 65536 || ny > 65536) return fail(1, "sdfnet_mc_classify: block larger than 65536 planes / rows");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CU(launch_mc_classify(sdf, nx, ny, nz, case_index, stream));
-  if (active_cells && n_active) {
-    const long total = static_cast<long>(nx - 1) * (ny - 1) * (nz - 1);
-    long* scratch = nullptr;
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(long) * (compact_num_blocks(total) + 1), stream));
-    static_assert(sizeof(long) == sizeof(int64_t), "LP64 expected");
-    cudaError_t e = launch_compact(case_index, total, 0, nullptr, reinterpret_cast<long*>(active_cells), nullptr,
-                                   reinterpret_cast<long*>(n_active), scratch, stream);
-    cudaFreeAsync(scratch, stream);
-    CU(e);
+  if (n_active) {
+    const int64_t total = static_cast<int64_t>(nx - 1) * (ny - 1) * (nz - 1);
+    return sdfnet_mc_compact(case_index, total, active_cells, n_active, stream_);
   }
+  return 0;
+}
+
+extern "C" int sdfnet_mc_compact(const uint8_t* case_index, int64_t n_cells, int64_t* active_cells, int64_t* n_active,
+                                 void* stream_) {
+  if (!case_index || !n_active) return fail(1, "sdfnet_mc_compact: null argument");
+  if (n_cells < 0) return fail(1, "sdfnet_mc_compact: negative cell count");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  static_assert(sizeof(long) == sizeof(int64_t), "LP64 expected");
+  long* scratch = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(long) * (compact_num_blocks(n_cells) + 1), stream));
+  cudaError_t e = active_cells
+                      ? launch_compact(case_index, n_cells, 0, nullptr, reinterpret_cast<long*>(active_cells), nullptr,
+                                       reinterpret_cast<long*>(n_active), scratch, stream)
+                      : launch_count_flags(case_index, n_cells, 0, reinterpret_cast<long*>(n_active), scratch, stream);
+  cudaFreeAsync(scratch, stream);
+  CU(e);
   return 0;
 }
 

@@ -71,15 +71,17 @@ def mc_classify(sdf_block, compact=True):
     nx, ny, nz = sdf_block.shape
     dev = sdf_block.device
     cases = torch.empty((nx - 1, ny - 1, nz - 1), dtype=torch.uint8, device=dev)
-    active = n_active = None
-    if compact:
-        active = torch.empty(cases.numel(), dtype=torch.int64, device=dev)
-        n_active = torch.zeros(1, dtype=torch.int64, device=dev)
+    active = None
+    n_active = torch.zeros(1, dtype=torch.int64, device=dev) if compact else None
     with torch.cuda.device(dev):
-        _lib.check(lib.sdfnet_mc_classify(_ptr(sdf_block), nx, ny, nz, _ptr(cases), _ptr(active), _ptr(n_active), _stream(dev)),
+        # classification + (compact) count of the active cells; the index list is then sized exactly
+        _lib.check(lib.sdfnet_mc_classify(_ptr(sdf_block), nx, ny, nz, _ptr(cases), _ptr(None), _ptr(n_active), _stream(dev)),
                    "sdfnet_mc_classify")
-    if compact:
-        active = active[: int(n_active.item())]
+        if compact:
+            active = torch.empty(int(n_active.item()), dtype=torch.int64, device=dev)
+            if active.numel():
+                _lib.check(lib.sdfnet_mc_compact(_ptr(cases), cases.numel(), _ptr(active), _ptr(n_active), _stream(dev)),
+                           "sdfnet_mc_compact")
     return cases, active
 
 
