@@ -12,4 +12,9 @@ for f in chain dw aux api; do
 done
 wait
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libsdfnet.so ../../build/chain.o ../../build/dw.o ../../build/aux.o ../../build/api.o -lcudart
+# native query tool (equivalent of the reference's ops/DeepTrace and ops/conversion_test programs)
+mkdir -p ../bin
+if [ ! -f ../bin/sdf_query ] || [ tools/sdf_query.cpp -nt ../bin/sdf_query ] || [ ../libsdfnet.so -nt ../bin/sdf_query ]; then
+  $NVCC -O2 -std=c++17 -o ../bin/sdf_query tools/sdf_query.cpp -L.. -lsdfnet -lcudart -Xlinker -rpath -Xlinker '$ORIGIN/..'
+fi
 echo "built $(cd .. && pwd)/libsdfnet.so"

@@ -84,3 +84,24 @@ def to_compatible_keys(state_dict):
         else:
             out[k] = v
     return out
+
+
+def export_flat(model, path):
+    """Write the network as an ``SDFW0001`` flat binary for the native query tool (``bin/sdf_query``, the equivalent of
+    the reference's ``utils/inference_conversion.py`` -> ``ops/DeepTrace`` / ``ops/conversion_test`` hand-off):
+    magic, int32 d_in / hidden / num_hidden / skip_layer, float32 beta, then per layer weight [out,in] and bias."""
+    import struct
+
+    net = model.module if hasattr(model, "module") else model
+    n_lin = net.num_layers - 1
+    hidden = getattr(net, "lin0").weight.shape[0]
+    skip = int(net.skip_in[0]) if len(net.skip_in) else 0
+    beta = float(getattr(net, "beta", 0.0) or 0.0)
+    with open(path, "wb") as f:
+        f.write(b"SDFW0001")
+        f.write(struct.pack("<4if", int(getattr(net, "lin0").weight.shape[1]), int(hidden), int(n_lin - 1), skip, beta))
+        for i in range(n_lin):
+            lin = getattr(net, f"lin{i}")
+            f.write(lin.weight.detach().float().cpu().contiguous().numpy().tobytes())
+            f.write(lin.bias.detach().float().cpu().contiguous().numpy().tobytes())
+    return path

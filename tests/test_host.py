@@ -143,3 +143,28 @@ def test_slab_and_row_sharding_cover_exactly():
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
     assert D.slab_bounds(1024, 3, 8) == (384, 512)
     assert D.world_size() == 1 and D.rank() == 0
+
+
+def test_export_flat_layout(tmp_path):
+    """SDFW0001 flat export read by the native query tool (csrc/tools/sdf_query.cpp): header + per-layer arrays."""
+    import struct
+
+    import numpy as np
+    import sdf_representation_b200 as pkg
+    from sdf_representation_b200 import checkpoint
+
+    torch.manual_seed(1)
+    net = pkg.ImplicitNet(3, [64] * 3, (2,), 100.0, True)
+    path = checkpoint.export_flat(net, str(tmp_path / "n.sdfw"))
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"SDFW0001"
+    d_in, hidden, nh, skip, beta = struct.unpack("<4if", raw[8:28])
+    assert (d_in, hidden, nh, skip) == (3, 64, 3, 2) and abs(beta - 100.0) < 1e-6
+    off = 28
+    for i in range(4):
+        lin = getattr(net, f"lin{i}")
+        for t in (lin.weight, lin.bias):
+            a = np.frombuffer(raw, dtype="<f4", count=t.numel(), offset=off)
+            assert np.array_equal(a, t.detach().numpy().reshape(-1))
+            off += 4 * t.numel()
+    assert off == len(raw)
