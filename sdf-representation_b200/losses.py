@@ -143,9 +143,16 @@ class WeightedSmoothL2Loss(nn.Module):
         return (w * (t - p) ** 2).mean()
 
 
-def get_points(pc_input, local_sigma=0.0001, generator=None):
-    """reference executor/executordistributed.py:108-123: a random third of the batch, perturbed by N(0, sigma^2)."""
+def get_points(pc_input, local_sigma=0.0001, generator=None, on_device=False):
+    """reference executor/executordistributed.py:108-123: a random third of the batch, perturbed by N(0, sigma^2).
+    Default: CPU randperm / randn exactly like the reference (same seeds -> same points).  ``on_device=True`` draws
+    the permutation and the noise with the device generator instead (no host work and no
+    H2D copy per step; a different random stream, same distribution)."""
     sample_size = pc_input.shape[0]
+    if on_device and pc_input.is_cuda:
+        perm = torch.randperm(sample_size, device=pc_input.device)[: sample_size // 3]
+        sample = pc_input[perm]
+        return sample + torch.randn_like(sample) * local_sigma
     perm = torch.randperm(sample_size, generator=generator)[: sample_size // 3]
     sample = pc_input[perm.to(pc_input.device)]
     noise = torch.randn(sample.shape, generator=generator, dtype=sample.dtype).to(pc_input.device)
