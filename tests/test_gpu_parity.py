@@ -394,6 +394,30 @@ def test_native_query_tool_matches_reference(tmp_path):
     assert ef < TOL_PARITY and eg < TOL_PARITY
 
 
+def test_training_is_independent_of_workspace_chunking(monkeypatch):
+    """A batch larger than the spill workspace is processed in chunks (odd tile counts, even-padded image arrays):
+    loss and every gradient must not depend on the chunk size."""
+    import sdf_representation_b200 as pkg
+    from sdf_representation_b200 import engine as eng_mod
+
+    def run(cap_bytes):
+        monkeypatch.setattr(eng_mod, "_WS_CAP_BYTES", cap_bytes)
+        torch.manual_seed(21)
+        net = pkg.ImplicitNet(3, [256] * 3, (2,), 100.0, True, precision="fast").to(dev())
+        g = torch.Generator().manual_seed(22)
+        x = torch.rand(20011, 3, generator=g) * 2 - 1
+        y = orc.torus_labels(x).float()
+        loss = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)(x.to(dev()), y.to(dev()), net, 0)
+        loss.backward()
+        return float(loss), torch.cat([p.grad.reshape(-1) for p in net.parameters()]).cpu()
+
+    l_one, g_one = run(8 << 30)
+    l_many, g_many = run(40 << 20)   # 40 MB: ~30 tiles of a 256-wide, 3-layer net per chunk -> 6 chunks
+    e = rel_err(g_many, g_one)
+    print(f"chunking: loss {l_one:.7f} vs {l_many:.7f}, grad rel diff {e:.3e}")
+    assert abs(l_one - l_many) < 1e-5 and e < 1e-4
+
+
 def test_octree_bit_exact_given_gpu_sdf():
     from sdf_representation_b200 import inference
 
