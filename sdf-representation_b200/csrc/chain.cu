@@ -258,7 +258,9 @@ struct EpiConst {
 #ifdef SDF_CLOCKS
   bool no_math, no_mufu, no_aux;  // FL_DBG_* measurement switches
 #endif
-  float sp[5];  // fast-mode softplus: log1p(e)/beta = e * (sp[0] + e (sp[1] + e (sp[2] + e (sp[3] + e sp[4]))))
+  // fast-mode softplus correction log1p(e)/beta = e (sp2[0] + e (sp2[1] + e (sp2[2] + e sp2[3]))), e = exp(-beta |z|),
+  // coefficients as packed 16-bit pairs (the arithmetic runs two elements per instruction)
+  uint32_t sp2[4];
 };
 
 // inputs / outputs of one step for this thread's tile
@@ -463,6 +465,21 @@ struct P2<DT_FP16> {
     asm("ex2.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a));
     return d;
   }
+  static __device__ __forceinline__ uint32_t fma(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+  }
+  static __device__ __forceinline__ uint32_t max(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  }
+  static __device__ __forceinline__ uint32_t abs(uint32_t a) {
+    uint32_t d;
+    asm("abs.f16x2 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+  }
 };
 template <>
 struct P2<DT_BF16> {
@@ -481,6 +498,21 @@ struct P2<DT_BF16> {
     asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
     return d;
   }
+  static __device__ __forceinline__ uint32_t fma(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+  }
+  static __device__ __forceinline__ uint32_t max(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  }
+  static __device__ __forceinline__ uint32_t abs(uint32_t a) {
+    uint32_t d;
+    asm("abs.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+  }
 };
 __device__ __forceinline__ uint32_t word(const uint4& u, int i) { return i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w)); }
 
@@ -492,25 +524,20 @@ __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& 
                                               uint32_t nbl2_2, bool has_b, uint4* ou) {
   uint32_t o[4];
   if (EPI == EPI_FWD_HIDDEN) {
+    // a = max(z, 0) + log1p(exp(-beta |z|)) / beta.  The correction is at most ln2 / beta and the result is rounded to
+    // 16 bits anyway, so it is evaluated on packed pairs: one MUFU (ex2) per element instead of ex2 + lg2 - the
+    // forward epilogue was MUFU-bound (ncu: mio-throttle stalls on every MUFU) - and a cubic on the FMA pipe.
     const float b[8] = {__uint_as_float(xa.x), __uint_as_float(xa.y), __uint_as_float(xa.z), __uint_as_float(xa.w),
                         __uint_as_float(xb.x), __uint_as_float(xb.y), __uint_as_float(xb.z), __uint_as_float(xb.w)};
-    float a[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float z = v[t] + b[t];
-#ifndef SDF_FWD_POLY
-      a[t] = softplus_k(z, k);  // ex2 + lg2 on the MUFU pipe (A/B on B200: 5 % faster than the polynomial log1p below)
-#else
-      const float e = ex2_approx(-fabsf(z * k.nbl2));
-      float pl = fmaf(e, k.sp[4], k.sp[3]);
-      pl = fmaf(e, pl, k.sp[2]);
-      pl = fmaf(e, pl, k.sp[1]);
-      pl = fmaf(e, pl, k.sp[0]);
-      a[t] = fmaf(e, pl, fmaxf(z, 0.f));
-#endif
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t zh = H16<DT>::pack(v[2 * i] + b[2 * i], v[2 * i + 1] + b[2 * i + 1]);
+      const uint32_t ex = P2<DT>::ex2(P2<DT>::mul(P2<DT>::abs(zh), nbl2_2));
+      uint32_t pl = P2<DT>::fma(ex, k.sp2[3], k.sp2[2]);
+      pl = P2<DT>::fma(pl, ex, k.sp2[1]);
+      pl = P2<DT>::fma(pl, ex, k.sp2[0]);
+      o[i] = P2<DT>::fma(pl, ex, P2<DT>::max(zh, 0u));
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = H16<DT>::pack(a[2 * i], a[2 * i + 1]);
   } else {
     uint32_t uo[4];
 #pragma unroll
@@ -579,8 +606,10 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("pre
 // Each thread owns 2 chunks of 32 columns per half (4 pieces of 16).  Every spill-image line the step will read is
 // first requested into L2 (prefetch.global.L2, while the MMAs of the step are still running); the four epilogue
 // warps of an SM sub-partition cover each other's load latencies.
+// Overlapped hidden-layer epilogue, loop form: one piece at a time, both halves share the code.  Used by the tangent /
+// adjoint sweeps (the software-pipelined form below spills in their piece loop and measured 16 % slower there).
 template <int DT, int EPI>
-__device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
+__device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
 #ifndef SDF_NO_L2PF
   // (same-session A/B on B200: +3 % for the tangent / adjoint sweeps, whose operands come from HBM; -2 % for the
@@ -703,10 +732,158 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #endif
 }
 
+// bit masks over the sweeps (1 forward, 2 reverse, 4 tangent, 8 adjoint): read the next accumulator piece / request the
+// next piece's spill-image operands one piece ahead
+#ifndef SDF_TMEM_AHEAD
+#define SDF_TMEM_AHEAD 15
+#endif
+#ifndef SDF_AUX_AHEAD
+#define SDF_AUX_AHEAD 14
+#endif
+template <int DT, int EPI>
+__device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
+                                                   uint32_t par0, uint32_t par1, float* gskip) {
+  constexpr bool kFwd = EPI == EPI_FWD_HIDDEN;
+  // Software pipeline of a warp (ncu: the sweeps that read spill images sat on the scoreboard of those loads, 60 % of
+  // the reverse epilogue's samples): the accumulator piece p + 1 is read from TMEM and the spill-image operands of
+  // piece p + 1 are requested while piece p is being processed.  The forward sweep's only memory operand is the bias
+  // row (L1-resident), loaded per piece.
+  constexpr int kSweepBit = EPI == EPI_FWD_HIDDEN ? 1 : EPI == EPI_REV_HIDDEN ? 2 : EPI == EPI_TAN_HIDDEN ? 4 : 8;
+  constexpr bool kTmemAhead = (SDF_TMEM_AHEAD & kSweepBit) != 0;
+  constexpr bool kAuxAhead = !kFwd && (SDF_AUX_AHEAD & kSweepBit) != 0;
+#ifndef SDF_NO_L2PF
+  // (same-session A/B on B200: +3 % for the tangent / adjoint sweeps, whose operands come from HBM; -2 % for the
+  // reverse sweep, whose activation images were written moments earlier and are mostly still in L2)
+  if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) {
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        prefetch_l2(io.in_a + img_off(ci * 128 + e.h * 32 + 8 * j, e.prow));
+        if (io.in_b) prefetch_l2(io.in_b + img_off(ci * 128 + e.h * 32 + 8 * j, e.prow));
+      }
+    }
+  }
+#endif
+  const uint32_t nbl2_2 = H16<DT>::pack(k.nbl2, k.nbl2);
+  const int cb = e.h * 32;  // this thread's column offset inside every 128-column block
+  Piece<false> xa[2], xb[2];
+  uint32_t r[2][16];
+  load_aux<false, EPI>(e, io, cb, xa[0], xb[0]);
+  CLK_DECL;
+  mbar_wait(&B.acc_full[0], par0);
+  tc_fence_after();
+  CLK_MARK(EPI, 0);
+  if (kTmemAhead) tmem_ld16(e.taddr + cb, r[0]);
+  // the tangent / adjoint sweeps keep the two halves as a loop: unrolled, their register pressure spills into the
+  // piece loop (measured: 16 % slower)
+  constexpr int kUnrollHalves = (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) ? 1 : 2;
+#pragma unroll kUnrollHalves
+  for (int half = 0; half < 2; ++half) {
+    if (half == 1) {
+      tmem_st_wait();
+      CLK_MARK(EPI, 1);
+      mbar_wait(&B.acc_full[1], par1);
+      tc_fence_after();
+      CLK_MARK(EPI, 2);
+      {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(e.taddr + cb, r0);
+        tmem_ld16(e.taddr + cb + 128, r1);
+        tmem_ld_wait();
+        if (kTmemAhead) tmem_ld16(e.taddr + 256 + cb, r[0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          st_smem_v4(e.sA + img_off(cb + 8 * j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
+          st_smem_v4(e.sA + img_off(cb + 128 + 8 * j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
+        }
+      }
+      fence_proxy_async_smem();
+      if (st.signal) {
+        tc_fence_before();
+        arrive_quarter(B, 0);
+        arrive_quarter(B, 1);
+      }
+      CLK_MARK(EPI, 3);
+    }
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      // piece pc of this half: chunk pc / 2, 16-column sub-piece pc % 2
+      const int cur = pc & 1, nxt = cur ^ 1;
+      const int c0 = half * 256 + (pc >> 1) * 128 + cb;  // chunk base column
+      const int c = c0 + (pc & 1) * 16;                  // first column of the piece
+      const int cn = pc < 3 ? half * 256 + ((pc + 1) >> 1) * 128 + cb + ((pc + 1) & 1) * 16 : 256 + cb;  // next piece
+      if (!kTmemAhead) tmem_ld16(e.taddr + c, r[cur]);
+      if (!kAuxAhead && (pc > 0 || half == 1)) load_aux<false, EPI>(e, io, c, xa[cur], xb[cur]);
+      tmem_ld_wait();
+      if (kTmemAhead && pc < 3) tmem_ld16(e.taddr + cn, r[nxt]);
+      if (kAuxAhead && (pc < 3 || half == 0)) load_aux<false, EPI>(e, io, cn, xa[nxt], xb[nxt]);
+      uint4 pq[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float w[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r[cur][8 * j + t]);
+        uint4 ou;
+        pq[j] = granule_fast<DT, EPI>(w, xa[cur].h[j], xb[cur].h[j], k, nbl2_2, io.in_b != nullptr, &ou);
+        if (EPI == EPI_TAN_HIDDEN) *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
+      }
+      const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
+      if (io.out) {
+        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = pq[0];
+        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = pq[1];
+      }
+      if (half == 0) {
+        tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
+      } else {
+        st_smem_v4(e.sA + img_off(c, e.prow), pq[0]);
+        st_smem_v4(e.sA + img_off(c + 8, e.prow), pq[1]);
+        if (pc == 1) {
+          // this thread's share of A columns [256,384) is written: the next GEMM may run two more weight chunks
+          fence_proxy_async_smem();
+          if (st.signal) arrive_quarter(B, 2);
+        }
+      }
+    }
+  }
+  if (io.special && cb + 32 == 128) {
+    // The last granule of this layer carries the raw input in its last three columns (skip injection, H = 512): redo
+    // it in the general form - accumulator half 1 is intact until quarter 3 is released - and overwrite what the
+    // loop above stored for it.  One granule of one layer; keeps the special case out of the piece loop.
+    const int c = k.H - 8;
+    uint32_t r8[8];
+    tmem_ld8(e.taddr + c, r8);
+    load_aux<false, EPI>(e, io, c - 8, xa[0], xb[0]);
+    tmem_ld_wait();
+    float w[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r8[t]);
+    granule_math<DT, false, EPI>(e, io, k, c, 1, w, xa[0], xb[0], gskip);
+    const uint4 pk = pack8<DT>(w);
+    if (io.out) *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = pk;
+    st_smem_v4(e.sA + img_off(c, e.prow), pk);
+  }
+  fence_proxy_async_smem();
+  if (st.signal) {
+    tc_fence_before();
+    arrive_quarter(B, 3);
+  }
+  CLK_MARK(EPI, 4);
+#ifdef SDF_CLOCKS
+  if (threadIdx.x == 0) e.clk[EPI * 8 + 5] += 1;
+#endif
+}
+
 template <int DT, bool PAR, int EPI>
 __device__ __forceinline__ void hidden_step(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                             uint32_t& n0, uint32_t& n1, float* gskip) {
-  if (!PAR && st.n_groups == 2) hidden_step_staged<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+  if (!PAR && st.n_groups == 2 && !k.relu) {
+#ifndef SDF_TA_PIPE
+#define SDF_TA_PIPE 0
+#endif
+    if (!SDF_TA_PIPE && (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN)) hidden_step_staged_v1<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+    else hidden_step_staged<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+  }
   else hidden_step_plain<DT, PAR, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
   ++n0;
   if (st.n_groups == 2) ++n1;
@@ -718,7 +895,10 @@ __device__ __forceinline__ void umma_any(uint32_t tmem_d, uint64_t da, uint64_t 
   else umma_f16_ss(tmem_d, da, db, idesc, accumulate);
 }
 
-template <int DT, bool PAR, bool PAIR>
+// SW: sweeps this instantiation can run (1 = forward / reverse programs, 2 = tangent / adjoint programs, 3 = both).  The
+// fast single-CTA kernel is instantiated per program family: half the code per kernel (the full kernel is ~10 k SASS
+// instructions, more than the instruction caches hold).
+template <int DT, bool PAR, bool PAIR, int SW>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
   using Cfg = ChainCfg<PAR, PAIR>;
   constexpr int NST = Cfg::kStages;
@@ -769,12 +949,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t ib = img_bytes(p.H);
 
-  // register file re-split (per SM sub-partition: 16384 registers = the CTA is launched with 640 x 96 registers; 128 x 40 + 512 x 104 fits that pool)
+  // register file re-split (per SM sub-partition: 16384 registers = the CTA is launched with 640 x 96 registers; 128 x 32 + 512 x 112 is exactly that pool)
   if (warp >= kEpiWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == kProducerWarp) {
-      // ------------------------------------------------------------------ weight producer
-      if (lane == 0) {
+      // ------------------------------------------------------------------ weight producer (warp-uniform loop, one
+      // elected lane issues the copies)
+      {
         uint32_t stage = 0, round = 0;
         for (int it = it0; it < it_end; it += it_step) {
           const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
@@ -784,17 +965,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             const int nchunks = st.n_groups * st.kchunks;
             const uint8_t* src = p.wpack + st.w_off;
             for (int c = 0; c < nchunks; ++c) {
-              mbar_wait(&w_empty[stage], (round & 1) ^ 1);
+              mbar_wait_vote(&w_empty[stage], (round & 1) ^ 1);
 #ifdef SDF_CLOCKS
               if (p.flags & FL_DBG_NO_W) {
-                mbar_arrive(&w_full[stage]);
+                if (elect_one()) mbar_arrive(&w_full[stage]);
               } else
 #endif
-              {
+              if (elect_one()) {
                 const uint32_t bytes = PAIR ? st.chunk_bytes / 2 : st.chunk_bytes;
                 mbar_arrive_expect_tx(&w_full[stage], bytes);
                 bulk_g2s(sW + stage * kStage, src + static_cast<size_t>(c) * st.chunk_bytes + rank * bytes, bytes, &w_full[stage]);
               }
+              __syncwarp();
               if (++stage == NST) { stage = 0; ++round; }
             }
           }
@@ -816,9 +998,91 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           }
         }
       }
+    } else if (warp == kMmaWarp && !PAIR) {
+      // ------------------------------------------------------------------ MMA issuer, single CTA.  ncu showed this
+      // warp busy ~90 % of the time on loop bookkeeping (~1150 cycles per weight chunk against 512 cycles of MMA
+      // work) while the epilogue warps waited for accumulators: the loop is the pacing resource of the kernel.  So:
+      // step fields are copied to locals once per step, chunk / quarter indices advance by counters (no division),
+      // descriptors advance by adds on their start-address field, barriers are addressed as integers, the loop stays
+      // warp-uniform (uniform registers) and one elected lane issues.
+      const uint32_t sA_d = smem_u32(sA) >> 4, sW_d = smem_u32(sW) >> 4;  // descriptor start-address units (16 B)
+      const uint32_t wfull_u = smem_u32(w_full), wempty_u = smem_u32(w_empty);
+      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q);
+      uint32_t stage = 0, wpar = 0, n0 = 0;
+      for (int it = it0; it < it_end; it += it_step) {
+        for (int s = 0; s < p.n_steps; ++s) {
+          const int n_groups = p.steps[s].n_groups;
+          if (n_groups == 0) continue;
+          const int ng = p.steps[s].ng, kchunks = p.steps[s].kchunks, a_chunks = p.steps[s].a_chunks;
+          const int k16 = p.steps[s].k16, k_lo = p.steps[s].k_lo;
+          const uint32_t par = n0 & 1;
+          const uint32_t idesc = make_idesc_f16(kTileRows, ng, DT == DT_BF16, false, false);
+          const uint32_t b_lbo = static_cast<uint32_t>(ng) * 16;  // rows of B x 16 B
+          const uint32_t db_step = (2 * b_lbo) >> 4;
+          const uint32_t a_chunk_d = (static_cast<uint32_t>(k16 * 2) * kGranuleBytes) >> 4;
+          const uint64_t da_hi = make_smem_desc(0, kGranuleBytes, 128);  // all fields but the start address
+          const uint64_t db_hi = make_smem_desc(0, b_lbo, 128);
+          for (int g = 0; g < n_groups; ++g) {
+            const uint32_t tmem_d = tmem_base + g * ng;
+            uint32_t a_d = sA_d;    // start-address field of the current A chunk (A chunk of weight chunk kc = kc % a_chunks)
+            int a_left = a_chunks;
+            int q = 0, q_left = 0;  // group 0: next A-image quarter to wait for, weight chunks until then
+            for (int kc = 0; kc < kchunks; ++kc) {
+              if (g == 0) {
+                // the A image becomes available quarter by quarter (hidden_step_staged)
+                if (k_lo == 0) {
+                  if (kc == 0) {
+                    for (int j = 0; j < 4; ++j) mbar_wait_vote_u32(aq_u + 8 * j, par, lane == 0);
+                    tc_fence_after();
+                  }
+                } else if (q < 4 && q_left == 0) {
+                  mbar_wait_vote_u32(aq_u + 8 * q, par, lane == 0);
+                  tc_fence_after();
+                  ++q;
+                  q_left = k_lo;
+                }
+                --q_left;
+              }
+              mbar_wait_vote_u32(wfull_u + 8 * stage, wpar, lane == 0);
+              tc_fence_after();
+              // descriptors of the chunk's first K = 16 slice; the following slices only advance the 14-bit start
+              // address fields (shared memory addresses stay below 2^18, so the adds never carry out of the field)
+              const uint64_t da0 = da_hi | a_d;
+              const uint64_t db0 = db_hi | (sW_d + stage * (kStage >> 4));
+              if (elect_one()) {
+#ifdef SDF_CLOCKS
+                if (!(p.flags & FL_DBG_NO_MMA))
+#endif
+                {
+                  if (k16 == 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16_ss(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                  (kc | k) != 0 ? 1u : 0u);
+                  } else {
+                    for (int k = 0; k < k16; ++k)
+                      umma_f16_ss(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                  (kc | k) != 0 ? 1u : 0u);
+                  }
+                }
+                umma_commit_u32(wempty_u + 8 * stage);
+                if (kc + 1 == kchunks) umma_commit_u32(accfull_u + 8 * g);
+              }
+              __syncwarp();
+              a_d += a_chunk_d;
+              if (--a_left == 0) { a_d = sA_d; a_left = a_chunks; }
+              if (++stage == NST) { stage = 0; wpar ^= 1; }
+            }
+          }
+          ++n0;
+        }
+      }
     } else if (warp == kMmaWarp) {
-      // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
-      if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer, CTA pair (leader CTA only).  The
+      // whole warp walks the loops and waits; one elected lane issues the MMAs and commits.
+      // Waits poll with one lane and a warp vote: 32 polling lanes are 32 barrier operations per poll and slowed the
+      // HBM-fed sweeps by 6 % (same-session A/B), a divergent single-lane wait loses the uniform loop.
+      {
         uint32_t stage = 0, round = 0, n0 = 0;
         const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
 #ifdef SDF_CLOCKS
@@ -847,40 +1111,45 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                   // the A image becomes available quarter by quarter (hidden_step_staged)
                   if (st.k_lo == 0) {
                     if (kc == 0) {
-                      ICLK(c_alo, for (int j = 0; j < 4; ++j) { if (PAIR) mbar_wait_cluster(&B.a_q[j], par); else mbar_wait(&B.a_q[j], par); })
+                      ICLK(c_alo, for (int j = 0; j < 4; ++j) { if (PAIR) mbar_wait_cluster(&B.a_q[j], par); else mbar_wait_vote(&B.a_q[j], par); })
                       tc_fence_after();
                     }
                   } else if (kc < 4 * st.k_lo && kc % st.k_lo == 0) {
-                    ICLK(c_ahi, if (PAIR) mbar_wait_cluster(&B.a_q[kc / st.k_lo], par); else mbar_wait(&B.a_q[kc / st.k_lo], par))
+                    ICLK(c_ahi, if (PAIR) mbar_wait_cluster(&B.a_q[kc / st.k_lo], par); else mbar_wait_vote(&B.a_q[kc / st.k_lo], par))
                     tc_fence_after();
                   }
                 }
-                ICLK(c_w, mbar_wait(&w_full[stage], round & 1); if (PAIR) mbar_wait_cluster(&peer_full[stage], round & 1))
+                ICLK(c_w, mbar_wait_vote(&w_full[stage], round & 1); if (PAIR) mbar_wait_cluster(&peer_full[stage], round & 1))
                 tc_fence_after();
                 // descriptors of the chunk's first K=16 slice; the following slices only advance the 14-bit start
                 // address fields (shared memory addresses stay below 2^18, so the adds never carry out of the field)
                 const uint64_t da0 = make_smem_desc(sA_u + a_idx * a_chunk_bytes, kGranuleBytes, 128);
                 const uint64_t db0 = make_smem_desc(sW_u + stage * kStage, b_lbo, 128);
                 if (++a_idx == static_cast<uint32_t>(st.a_chunks)) a_idx = 0;
+                if (elect_one()) {
 #ifdef SDF_CLOCKS
-                if (!(p.flags & FL_DBG_NO_MMA))
+                  if (!(p.flags & FL_DBG_NO_MMA))
 #endif
-                {
-                  if (st.k16 == (PAIR ? 8 : 4)) {
+                  {
+                    if (st.k16 == (PAIR ? 8 : 4)) {
 #pragma unroll
-                    for (int k = 0; k < (PAIR ? 8 : 4); ++k)
-                      umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
-                                     (kc | k) != 0 ? 1u : 0u);
-                  } else {
-                    for (int k = 0; k < st.k16; ++k)
-                      umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
-                                     (kc | k) != 0 ? 1u : 0u);
+                      for (int k = 0; k < (PAIR ? 8 : 4); ++k)
+                        umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                       (kc | k) != 0 ? 1u : 0u);
+                    } else {
+                      for (int k = 0; k < st.k16; ++k)
+                        umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                       (kc | k) != 0 ? 1u : 0u);
+                    }
+                  }
+                  if (PAIR) umma_commit2(&w_empty[stage], 3); else umma_commit(&w_empty[stage]);
+                  if (kc + 1 == st.kchunks) {
+                    if (PAIR) umma_commit2(&B.acc_full[g], 3); else umma_commit(&B.acc_full[g]);
                   }
                 }
-                if (PAIR) umma_commit2(&w_empty[stage], 3); else umma_commit(&w_empty[stage]);
+                __syncwarp();
                 if (++stage == NST) { stage = 0; ++round; }
               }
-              if (PAIR) umma_commit2(&B.acc_full[g], 3); else umma_commit(&B.acc_full[g]);
             }
             ++n0;
 #ifdef SDF_CLOCKS
@@ -890,7 +1159,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         }
 #ifdef SDF_CLOCKS
         c_tot = clock64() - c_begin;
-        if (p.dbg_clk) {
+        if (p.dbg_clk && lane == 0) {
           unsigned long long* d = reinterpret_cast<unsigned long long*>(p.dbg_clk) + 64;
           atomicAdd(d + 0, static_cast<unsigned long long>(c_alo));
           atomicAdd(d + 1, static_cast<unsigned long long>(c_ahi));
@@ -903,7 +1172,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     Epi e;
     e.sA = smem_u32(sA);
     const int q = warp & 3;
@@ -935,11 +1204,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     constexpr bool no_stg = false;
 #endif
     {
-      // log1p(x) = x P(x) on [0,1], |error| < 4.1e-5 (degree-4 Chebyshev fit): 4e-7 after the 1/beta scale, an
-      // order of magnitude under the 16-bit rounding of the stored activation
-      const float c[5] = {0.9999449849128723f, -0.4970308542251587f, 0.30656111240386963f, -0.157838374376297f, 0.04155111312866211f};
+      // log1p(x) = x P(x) on [0,1], cubic P, |error| < 7.1e-5 (6.4e-4 when evaluated in fp16): after the 1/beta scale
+      // an order of magnitude under the 16-bit rounding of the stored activation
+      const float c[4] = {0.99744897f, -0.4713013f, 0.22568572f, -0.05875714f};
 #pragma unroll
-      for (int i = 0; i < 5; ++i) k.sp[i] = c[i] * p.inv_beta;
+      for (int i = 0; i < 4; ++i) k.sp2[i] = H16<DT>::pack(c[i] * p.inv_beta, c[i] * p.inv_beta);
     }
     const bool relu = k.relu;
     const float mult = p.seed_mult ? __ldg(p.seed_mult) : 1.f;
@@ -957,7 +1226,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       // write its two granules)
       const int first = p.steps[0].epi;
       e.x[0] = e.x[1] = e.x[2] = 0.f;
-      if (first == EPI_FWD_HIDDEN) {
+      const bool fwd_program = SW == 1 || (SW == 3 && first == EPI_FWD_HIDDEN);
+      if (fwd_program) {
         if (e.math) {
           if (e.valid) {
             if (p.src == SRC_POINTS) {
@@ -1034,13 +1304,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         io.vec = nullptr;
         io.special = false;
         switch (st.epi) {
-          case EPI_FWD_HIDDEN: {
+          case EPI_FWD_HIDDEN: if (SW & 1) {
             io.out = ((p.flags & FL_SPILL_A) && !no_stg) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
             io.vec = p.bias + l * p.H;
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_FWD_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
-          case EPI_FWD_LAST: {
+          case EPI_FWD_LAST: if (SW & 1) {
             mbar_wait(&B.acc_full[0], n0 & 1);
             tc_fence_after();
             ++n0;
@@ -1055,7 +1325,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               }
             }
           } break;
-          case EPI_REV_START: {
+          case EPI_REV_START: if (SW & 1) {
             // q_{L-1} = w_L * act'(z_{L-1}); the A image still holds a_{L-1}
             uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l, p.tile_stride, tile, ib) : nullptr;
             if (e.math) {
@@ -1081,14 +1351,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               arrive_all_quarters(B);
             }
           } break;
-          case EPI_REV_HIDDEN: {
+          case EPI_REV_HIDDEN: if (SW & 1) {
             // GEMM r = q_l W_l done; q_{l-1} = r * act'(z_{l-1});  l = st.layer
             io.in_a = img_ptr(p.Aimg, l - 1, p.tile_stride, tile, ib);
             io.out = ((p.flags & FL_SPILL_Q) && !no_stg) ? img_ptr(p.Qimg, l - 1, p.tile_stride, tile, ib) : nullptr;
             io.special = (l - 1) == inj_layer;
             hidden_step<DT, PAR, EPI_REV_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
-          case EPI_REV_LAST: {
+          case EPI_REV_LAST: if (SW & 1) {
             mbar_wait(&B.acc_full[0], n0 & 1);
             tc_fence_after();
             ++n0;
@@ -1112,7 +1382,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             }
             named_bar_sync(1, kEpiThreads);  // gskip may be rewritten by the next tile
           } break;
-          case EPI_TAN_HIDDEN: {
+          case EPI_TAN_HIDDEN: if (SW & 2) {
             io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
             io.in_b = relu ? nullptr : img_ptr(p.Qimg, l, p.tile_stride, tile, ib);
             io.out = no_stg ? nullptr : img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
@@ -1120,7 +1390,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_TAN_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
-          case EPI_ADJ_START: {
+          case EPI_ADJ_START: if (SW & 2) {
             // Zbar_{L-1} = s' * (w_L fbar) + u_{L-1}
             const uint8_t* aimg = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
             const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.tile_stride, tile, ib) : nullptr;
@@ -1159,7 +1429,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               arrive_all_quarters(B);
             }
           } break;
-          case EPI_ADJ_HIDDEN: {
+          case EPI_ADJ_HIDDEN: if (SW & 2) {
             io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
             io.in_b = has_u ? img_ptr(p.Uimg, l, p.tile_stride, tile, ib) : nullptr;
             io.out = no_stg ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
@@ -1188,10 +1458,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int DT, bool PAR, bool PAIR>
+template <int DT, bool PAR, bool PAIR, int SW = 3>
 static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kfn = chain_kernel<DT, PAR, PAIR>;
+  auto kfn = chain_kernel<DT, PAR, PAIR, SW>;
   constexpr uint32_t smem = ChainCfg<PAR, PAIR>::kSmem;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1250,7 +1520,12 @@ cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int pair, 
   if (p.n_tiles <= 0) return cudaSuccess;
   if (parity) return dtype == DT_BF16 ? launch_one<DT_BF16, true, false>(p, num_sms, stream) : launch_one<DT_FP16, true, false>(p, num_sms, stream);
   if (pair) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true>(p, num_sms, stream) : launch_one<DT_FP16, false, true>(p, num_sms, stream);
-  return dtype == DT_BF16 ? launch_one<DT_BF16, false, false>(p, num_sms, stream) : launch_one<DT_FP16, false, false>(p, num_sms, stream);
+  // program family of this launch (api.cu builds forward [+ reverse] programs or tangent / adjoint programs)
+  bool fr = false, ta = false;
+  for (int s = 0; s < p.n_steps; ++s) (p.steps[s].epi <= EPI_REV_LAST ? fr : ta) = true;
+  if (fr && !ta) return dtype == DT_BF16 ? launch_one<DT_BF16, false, false, 1>(p, num_sms, stream) : launch_one<DT_FP16, false, false, 1>(p, num_sms, stream);
+  if (ta && !fr) return dtype == DT_BF16 ? launch_one<DT_BF16, false, false, 2>(p, num_sms, stream) : launch_one<DT_FP16, false, false, 2>(p, num_sms, stream);
+  return dtype == DT_BF16 ? launch_one<DT_BF16, false, false, 3>(p, num_sms, stream) : launch_one<DT_FP16, false, false, 3>(p, num_sms, stream);
 }
 
 }  // namespace sdf

@@ -187,6 +187,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // tcgen05.st 32x32b.x16: thread i of the warp writes lane base+i, registers j -> consecutive columns
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -203,6 +209,50 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One lane of the (fully active) warp.  Single-thread roles (TMA producer, MMA issuer) keep their loops warp-uniform
+// and predicate only the issuing instructions with this: the loop scalars then live in uniform registers and a
+// tcgen05.mma costs one instruction instead of ~25 (measured with tools/ring_probe.cu: 234 -> 138 cycles per
+// M128 N256 K16 MMA through a 3 x 32 KB ring).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// Warp-uniform wait: lane 0 polls (predicated try_wait, no divergent region), the warp votes on the outcome.
+__device__ __forceinline__ void mbar_wait_vote(uint64_t* bar, uint32_t parity) {
+  const bool poller = (threadIdx.x & 31) == 0;
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok = 0;
+    if (poller) ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+    if (__any_sync(0xffffffffu, ok != 0)) break;
+    if (++spins > SDF_SPIN_LIMIT) __trap();
+  }
+}
+
+// the same on a shared-memory address (issue loops keep barrier addresses as integers)
+__device__ __forceinline__ void mbar_wait_vote_u32(uint32_t bar_addr, uint32_t parity, bool poller) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok = 0;
+    if (poller) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+    }
+    if (__any_sync(0xffffffffu, ok != 0)) break;
+    if (++spins > SDF_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -1,7 +1,9 @@
 // Probe: does concurrent epilogue-style traffic from other warps slow tcgen05.mma (M=128, N=256, K=16, SS)?
 //   mma_contend <bg mask> <iters>
 //   bg bits: 1 = tcgen05.ld x16 loop on the other accumulator half, 2 = st.shared.v4 loop into a scratch region,
-//            4 = tcgen05.st x8 loop, 8 = FP32/MUFU arithmetic loop, 16 = mbarrier try_wait polling loop
+//            4 = tcgen05.st x8 loop, 8 = FP32/MUFU arithmetic loop, 16 = mbarrier try_wait polling loop,
+//            32 = one warp streams 32 KB bulk copies (TMA) from global memory into an unused shared-memory stage,
+//            64 = operands filled with pseudo-random fp16 data instead of zeros
 // 1 issuer warp + 16 background warps (lane quarter = warp % 4).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/mma_contend tools/mma_contend.cu
 #include <cstdio>
@@ -9,16 +11,22 @@
 #include "../sdf-representation_b200/csrc/ptx.cuh"
 using namespace sdf;
 
-__global__ void __launch_bounds__(544, 1) contend_kernel(int bg, int iters, long long* cycles, float* sink) {
+__global__ void __launch_bounds__(544, 1) contend_kernel(int bg, int iters, long long* cycles, float* sink, const uint8_t* gsrc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar, pollbar;
   __shared__ uint32_t slot;
   __shared__ volatile int stop;
-  for (uint32_t i = threadIdx.x; i < 196608 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = threadIdx.x; i < 196608 / 16; i += blockDim.x) {
+    uint32_t v = 0;
+    if (bg & 64) { v = (i * 2654435761u) ^ (i >> 3); v = (v & 0x03ff03ffu) | 0x38003800u; }  // fp16 values in [0.5, 1)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(v, v * 3u & 0x3bff3bffu | 0x38003800u, v ^ 0x00550055u, v);
+  }
+  __shared__ uint64_t tbar;
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     mbar_init(&pollbar, 1);
+    mbar_init(&tbar, 1);
     mbar_fence_init();
     stop = 0;
   }
@@ -48,6 +56,16 @@ __global__ void __launch_bounds__(544, 1) contend_kernel(int bg, int iters, long
       long long t1 = clock64();
       cycles[blockIdx.x] = t1 - t0;
       stop = 1;
+    }
+  } else if (warp == 16 && (bg & 32)) {
+    if (lane == 0) {
+      uint32_t ph = 0;
+      while (!stop) {
+        mbar_arrive_expect_tx(&tbar, 32768);
+        bulk_g2s(smem + 131072 + 32768, gsrc + (blockIdx.x & 63) * 32768, 32768, &tbar);
+        mbar_wait(&tbar, ph & 1);
+        ++ph;
+      }
     }
   } else {
     const int q = (warp - 1) & 3;
@@ -101,14 +119,17 @@ int main(int argc, char** argv) {
   float* sink;
   cudaMalloc(&d, sizeof(long long) * 148);
   cudaMalloc(&sink, sizeof(float) * 1024);
+  uint8_t* gsrc;
+  cudaMalloc(&gsrc, 64 * 32768);
+  cudaMemset(gsrc, 0x3c, 64 * 32768);
   cudaFuncSetAttribute(contend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
-  contend_kernel<<<148, 544, 196608>>>(bg, 10, d, sink);
+  contend_kernel<<<148, 544, 196608>>>(bg, 10, d, sink, gsrc);
   cudaDeviceSynchronize();
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  contend_kernel<<<148, 544, 196608>>>(bg, iters, d, sink);
+  contend_kernel<<<148, 544, 196608>>>(bg, iters, d, sink, gsrc);
   cudaEventRecord(e1);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("mma_contend bg=%d: CUDA error %s\n", bg, cudaGetErrorString(e)); return 1; }
