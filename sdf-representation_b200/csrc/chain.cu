@@ -51,6 +51,15 @@ namespace sdf {
 #define CLK_MARK(kind, phase)
 #endif
 
+// register split between the epilogue warps and the producer / issuer warpgroup (640 x 96 = 61440 registers in all)
+#ifndef SDF_REGS_EPI
+#define SDF_REGS_EPI 104
+#define SDF_REGS_AUX 56
+#endif
+#ifndef SDF_ISSUER_UNROLL
+#define SDF_ISSUER_UNROLL 1
+#endif
+
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kProducerWarp = kEpiWarps;
@@ -949,9 +958,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t ib = img_bytes(p.H);
 
-  // register file re-split (per SM sub-partition: 16384 registers = the CTA is launched with 640 x 96 registers; 128 x 32 + 512 x 112 is exactly that pool)
+  // register file re-split (per SM sub-partition: 16384 registers = the CTA is launched with 640 x 96 registers; 128 x 56 + 512 x 104 fits that pool)
   if (warp >= kEpiWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SDF_REGS_AUX));
     if (warp == kProducerWarp) {
       // ------------------------------------------------------------------ weight producer (warp-uniform loop, one
       // elected lane issues the copies)
@@ -1009,6 +1018,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       const uint32_t wfull_u = smem_u32(w_full), wempty_u = smem_u32(w_empty);
       const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q);
       uint32_t stage = 0, wpar = 0, n0 = 0;
+      const bool poller = elect_one();  // (opaque to the compiler: a predicate it keeps instead of re-deriving the lane)
       for (int it = it0; it < it_end; it += it_step) {
         for (int s = 0; s < p.n_steps; ++s) {
           const int n_groups = p.steps[s].n_groups;
@@ -1022,6 +1032,49 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           const uint32_t a_chunk_d = (static_cast<uint32_t>(k16 * 2) * kGranuleBytes) >> 4;
           const uint64_t da_hi = make_smem_desc(0, kGranuleBytes, 128);  // all fields but the start address
           const uint64_t db_hi = make_smem_desc(0, b_lbo, 128);
+          if (SDF_ISSUER_UNROLL && k16 == 4 && kchunks == 8 && a_chunks == 8 && n_groups == 2) {
+            // The hot shape (512 x 512 layer, fast mode): both column groups and their 8 weight chunks unrolled, so
+            // chunk indices, accumulate flags and A-descriptor offsets are immediates; only the ring stage is state.
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint32_t tmem_d = tmem_base + g * ng;
+#pragma unroll
+              for (int kc = 0; kc < 8; ++kc) {
+                if (g == 0) {
+                  if (k_lo == 0) {
+                    if (kc == 0) {
+                      for (int j = 0; j < 4; ++j) mbar_wait_vote_u32(aq_u + 8 * j, par, poller);
+                      tc_fence_after();
+                    }
+                  } else if ((kc & 1) == 0) {  // k_lo == 2: two weight chunks per 128-column quarter
+                    mbar_wait_vote_u32(aq_u + 8 * (kc >> 1), par, poller);
+                    tc_fence_after();
+                  }
+                }
+                mbar_wait_vote_u32(wfull_u + 8 * stage, wpar, poller);
+                tc_fence_after();
+                const uint64_t da0 = da_hi | (sA_d + kc * ((4 * 2 * kGranuleBytes) >> 4));
+                const uint64_t db0 = db_hi | (sW_d + stage * (kStage >> 4));
+                if (elect_one()) {
+#ifdef SDF_CLOCKS
+                  if (!(p.flags & FL_DBG_NO_MMA))
+#endif
+                  {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16_ss(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                  (kc | k) != 0 ? 1u : 0u);
+                  }
+                  umma_commit_u32(wempty_u + 8 * stage);
+                  if (kc == 7) umma_commit_u32(accfull_u + 8 * g);
+                }
+                __syncwarp();
+                if (++stage == NST) { stage = 0; wpar ^= 1; }
+              }
+            }
+            ++n0;
+            continue;
+          }
           for (int g = 0; g < n_groups; ++g) {
             const uint32_t tmem_d = tmem_base + g * ng;
             uint32_t a_d = sA_d;    // start-address field of the current A chunk (A chunk of weight chunk kc = kc % a_chunks)
@@ -1032,18 +1085,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                 // the A image becomes available quarter by quarter (hidden_step_staged)
                 if (k_lo == 0) {
                   if (kc == 0) {
-                    for (int j = 0; j < 4; ++j) mbar_wait_vote_u32(aq_u + 8 * j, par, lane == 0);
+                    for (int j = 0; j < 4; ++j) mbar_wait_vote_u32(aq_u + 8 * j, par, poller);
                     tc_fence_after();
                   }
                 } else if (q < 4 && q_left == 0) {
-                  mbar_wait_vote_u32(aq_u + 8 * q, par, lane == 0);
+                  mbar_wait_vote_u32(aq_u + 8 * q, par, poller);
                   tc_fence_after();
                   ++q;
                   q_left = k_lo;
                 }
                 --q_left;
               }
-              mbar_wait_vote_u32(wfull_u + 8 * stage, wpar, lane == 0);
+              mbar_wait_vote_u32(wfull_u + 8 * stage, wpar, poller);
               tc_fence_after();
               // descriptors of the chunk's first K = 16 slice; the following slices only advance the 14-bit start
               // address fields (shared memory addresses stay below 2^18, so the adds never carry out of the field)
@@ -1172,7 +1225,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SDF_REGS_EPI));
     Epi e;
     e.sA = smem_u32(sA);
     const int q = warp & 3;
