@@ -749,6 +749,10 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
 #ifndef SDF_AUX_AHEAD
 #define SDF_AUX_AHEAD 14
 #endif
+// sweeps (same bit mask) whose spill-image operands are requested two pieces ahead instead of one (unrolled halves only)
+#ifndef SDF_AUX_DIST2
+#define SDF_AUX_DIST2 0
+#endif
 template <int DT, int EPI>
 __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
@@ -760,6 +764,8 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
   constexpr int kSweepBit = EPI == EPI_FWD_HIDDEN ? 1 : EPI == EPI_REV_HIDDEN ? 2 : EPI == EPI_TAN_HIDDEN ? 4 : 8;
   constexpr bool kTmemAhead = (SDF_TMEM_AHEAD & kSweepBit) != 0;
   constexpr bool kAuxAhead = !kFwd && (SDF_AUX_AHEAD & kSweepBit) != 0;
+  constexpr int kUnrollHalves = (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) ? 1 : 2;
+  constexpr int kAuxDist = !kAuxAhead ? 0 : ((SDF_AUX_DIST2 & kSweepBit) != 0 && kUnrollHalves == 2) ? 2 : 1;
 #ifndef SDF_NO_L2PF
   // (same-session A/B on B200: +3 % for the tangent / adjoint sweeps, whose operands come from HBM; -2 % for the
   // reverse sweep, whose activation images were written moments earlier and are mostly still in L2)
@@ -776,9 +782,10 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #endif
   const uint32_t nbl2_2 = H16<DT>::pack(k.nbl2, k.nbl2);
   const int cb = e.h * 32;  // this thread's column offset inside every 128-column block
-  Piece<false> xa[2], xb[2];
+  Piece<false> xa[3], xb[3];
   uint32_t r[2][16];
   load_aux<false, EPI>(e, io, cb, xa[0], xb[0]);
+  if (kAuxDist == 2) load_aux<false, EPI>(e, io, cb + 16, xa[1], xb[1]);
   CLK_DECL;
   mbar_wait(&B.acc_full[0], par0);
   tc_fence_after();
@@ -786,7 +793,6 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
   if (kTmemAhead) tmem_ld16(e.taddr + cb, r[0]);
   // the tangent / adjoint sweeps keep the two halves as a loop: unrolled, their register pressure spills into the
   // piece loop (measured: 16 % slower)
-  constexpr int kUnrollHalves = (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) ? 1 : 2;
 #pragma unroll kUnrollHalves
   for (int half = 0; half < 2; ++half) {
     if (half == 1) {
@@ -818,15 +824,21 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #pragma unroll
     for (int pc = 0; pc < 4; ++pc) {
       // piece pc of this half: chunk pc / 2, 16-column sub-piece pc % 2
+      const int P = half * 4 + pc;  // piece index of the step (compile-time when the halves are unrolled)
       const int cur = pc & 1, nxt = cur ^ 1;
+      const int ac = kAuxDist == 2 ? P % 3 : cur;  // buffer holding this piece's spill-image operands
       const int c0 = half * 256 + (pc >> 1) * 128 + cb;  // chunk base column
       const int c = c0 + (pc & 1) * 16;                  // first column of the piece
       const int cn = pc < 3 ? half * 256 + ((pc + 1) >> 1) * 128 + cb + ((pc + 1) & 1) * 16 : 256 + cb;  // next piece
       if (!kTmemAhead) tmem_ld16(e.taddr + c, r[cur]);
-      if (!kAuxAhead && (pc > 0 || half == 1)) load_aux<false, EPI>(e, io, c, xa[cur], xb[cur]);
+      if (!kAuxAhead && (pc > 0 || half == 1)) load_aux<false, EPI>(e, io, c, xa[ac], xb[ac]);
       tmem_ld_wait();
       if (kTmemAhead && pc < 3) tmem_ld16(e.taddr + cn, r[nxt]);
-      if (kAuxAhead && (pc < 3 || half == 0)) load_aux<false, EPI>(e, io, cn, xa[nxt], xb[nxt]);
+      if (kAuxDist == 1 && (pc < 3 || half == 0)) load_aux<false, EPI>(e, io, cn, xa[nxt], xb[nxt]);
+      if (kAuxDist == 2 && P + 2 < 8) {
+        const int P2 = P + 2;
+        load_aux<false, EPI>(e, io, (P2 >> 2) * 256 + ((P2 & 3) >> 1) * 128 + cb + (P2 & 1) * 16, xa[P2 % 3], xb[P2 % 3]);
+      }
       uint4 pq[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -834,7 +846,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #pragma unroll
         for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r[cur][8 * j + t]);
         uint4 ou;
-        pq[j] = granule_fast<DT, EPI>(w, xa[cur].h[j], xb[cur].h[j], k, nbl2_2, io.in_b != nullptr, &ou);
+        pq[j] = granule_fast<DT, EPI>(w, xa[ac].h[j], xb[ac].h[j], k, nbl2_2, io.in_b != nullptr, &ou);
         if (EPI == EPI_TAN_HIDDEN) *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
       }
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
