@@ -56,10 +56,14 @@ namespace sdf {
 #define SDF_REGS_EPI 104
 #define SDF_REGS_AUX 56
 #endif
+#ifndef SDF_COPY_SPLIT
+#define SDF_COPY_SPLIT 1
+#endif
 #ifndef SDF_ISSUER_UNROLL
 #define SDF_ISSUER_UNROLL 1
 #endif
 
+constexpr int kCopySplit = SDF_COPY_SPLIT;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kProducerWarp = kEpiWarps;
@@ -995,7 +999,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               if (elect_one()) {
                 const uint32_t bytes = PAIR ? st.chunk_bytes / 2 : st.chunk_bytes;
                 mbar_arrive_expect_tx(&w_full[stage], bytes);
-                bulk_g2s(sW + stage * kStage, src + static_cast<size_t>(c) * st.chunk_bytes + rank * bytes, bytes, &w_full[stage]);
+                // one stage = kCopySplit concurrent bulk copies (a single copy does not saturate the L2 -> SM path)
+                const uint32_t part = bytes / kCopySplit;
+                const uint8_t* gsrc = src + static_cast<size_t>(c) * st.chunk_bytes + rank * bytes;
+                if ((part & 15u) == 0) {
+#pragma unroll
+                  for (int i = 0; i < kCopySplit; ++i) bulk_g2s(sW + stage * kStage + i * part, gsrc + i * part, part, &w_full[stage]);
+                } else {
+                  bulk_g2s(sW + stage * kStage, gsrc, bytes, &w_full[stage]);
+                }
               }
               __syncwarp();
               if (++stage == NST) { stage = 0; ++round; }
@@ -1143,96 +1155,106 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         }
       }
     } else if (warp == kMmaWarp) {
-      // ------------------------------------------------------------------ MMA issuer, CTA pair (leader CTA only).  The
-      // whole warp walks the loops and waits; one elected lane issues the MMAs and commits.
-      // Waits poll with one lane and a warp vote: 32 polling lanes are 32 barrier operations per poll and slowed the
-      // HBM-fed sweeps by 6 % (same-session A/B), a divergent single-lane wait loses the uniform loop.
-      {
-        uint32_t stage = 0, round = 0, n0 = 0;
-        const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
-#ifdef SDF_CLOCKS
-        long long c_alo = 0, c_ahi = 0, c_w = 0, c_tot = 0, c_steps = 0;
-        const long long c_begin = clock64();
-#define ICLK(var, stmt) { const long long t_ = clock64(); stmt; var += clock64() - t_; }
-#else
-#define ICLK(var, stmt) stmt;
-#endif
-        for (int it = it0; it < it_end; it += it_step) {
-          const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
-          (void)tile;
-          for (int s = 0; s < p.n_steps; ++s) {
-            const StepDesc& st = p.steps[s];
-            if (st.n_groups == 0) continue;
-            const uint32_t par = n0 & 1;
-            const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTileRows : kTileRows, st.ng, DT == DT_BF16, false, false);
-            const uint32_t b_lbo = static_cast<uint32_t>(PAIR ? st.ng / 2 : st.ng) * 16;  // rows of B in this CTA x 16 B
-            const uint64_t db_step = (2 * b_lbo) >> 4;
-            const uint32_t a_chunk_bytes = static_cast<uint32_t>(st.k16 * 2) * kGranuleBytes;
-            for (int g = 0; g < st.n_groups; ++g) {
-              const uint32_t tmem_d = tmem_base + g * st.ng;
-              uint32_t a_idx = 0;  // A chunk of weight chunk kc = kc % a_chunks
-              for (int kc = 0; kc < st.kchunks; ++kc) {
+      // ------------------------------------------------------------------ MMA issuer, CTA pair (leader CTA), lean form
+      // of the loop above: M = 256 MMAs over both CTAs' tiles, 8 per weight chunk (K = 128), so the issue cost per
+      // FLOP and the L2 -> SM weight bytes per SM are half of the single-CTA kernel's and a ring stage holds twice the
+      // tensor time.
+      const uint32_t sA_d = smem_u32(sA) >> 4, sW_d = smem_u32(sW) >> 4;
+      const uint32_t wfull_u = smem_u32(w_full), wempty_u = smem_u32(w_empty), pfull_u = smem_u32(peer_full);
+      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q);
+      uint32_t stage = 0, wpar = 0, n0 = 0;
+      const bool poller = elect_one();
+      for (int it = it0; it < it_end; it += it_step) {
+        for (int s = 0; s < p.n_steps; ++s) {
+          const int n_groups = p.steps[s].n_groups;
+          if (n_groups == 0) continue;
+          const int ng = p.steps[s].ng, kchunks = p.steps[s].kchunks, a_chunks = p.steps[s].a_chunks;
+          const int k16 = p.steps[s].k16, k_lo = p.steps[s].k_lo;
+          const uint32_t par = n0 & 1;
+          const uint32_t idesc = make_idesc_f16(2 * kTileRows, ng, DT == DT_BF16, false, false);
+          const uint32_t b_lbo = static_cast<uint32_t>(ng / 2) * 16;  // rows of B in this CTA x 16 B
+          const uint32_t db_step = (2 * b_lbo) >> 4;
+          const uint32_t a_chunk_d = (static_cast<uint32_t>(k16 * 2) * kGranuleBytes) >> 4;
+          const uint64_t da_hi = make_smem_desc(0, kGranuleBytes, 128);
+          const uint64_t db_hi = make_smem_desc(0, b_lbo, 128);
+          if (k16 == 8 && kchunks == 4 && a_chunks == 4 && n_groups == 2 && k_lo <= 1) {
+            // hot shape (512 x 512 layer): 2 column groups x 4 weight chunks, unrolled
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint32_t tmem_d = tmem_base + g * ng;
+#pragma unroll
+              for (int kc = 0; kc < 4; ++kc) {
                 if (g == 0) {
-                  // the A image becomes available quarter by quarter (hidden_step_staged)
-                  if (st.k_lo == 0) {
+                  if (k_lo == 0) {
                     if (kc == 0) {
-                      ICLK(c_alo, for (int j = 0; j < 4; ++j) { if (PAIR) mbar_wait_cluster(&B.a_q[j], par); else mbar_wait_vote(&B.a_q[j], par); })
+                      for (int j = 0; j < 4; ++j) mbar_wait_cluster_vote_u32(aq_u + 8 * j, par, poller);
                       tc_fence_after();
                     }
-                  } else if (kc < 4 * st.k_lo && kc % st.k_lo == 0) {
-                    ICLK(c_ahi, if (PAIR) mbar_wait_cluster(&B.a_q[kc / st.k_lo], par); else mbar_wait_vote(&B.a_q[kc / st.k_lo], par))
+                  } else {  // one weight chunk per 128-column quarter of the A images
+                    mbar_wait_cluster_vote_u32(aq_u + 8 * kc, par, poller);
                     tc_fence_after();
                   }
                 }
-                ICLK(c_w, mbar_wait_vote(&w_full[stage], round & 1); if (PAIR) mbar_wait_cluster(&peer_full[stage], round & 1))
+                mbar_wait_vote_u32(wfull_u + 8 * stage, wpar, poller);
+                mbar_wait_cluster_vote_u32(pfull_u + 8 * stage, wpar, poller);
                 tc_fence_after();
-                // descriptors of the chunk's first K=16 slice; the following slices only advance the 14-bit start
-                // address fields (shared memory addresses stay below 2^18, so the adds never carry out of the field)
-                const uint64_t da0 = make_smem_desc(sA_u + a_idx * a_chunk_bytes, kGranuleBytes, 128);
-                const uint64_t db0 = make_smem_desc(sW_u + stage * kStage, b_lbo, 128);
-                if (++a_idx == static_cast<uint32_t>(st.a_chunks)) a_idx = 0;
+                const uint64_t da0 = da_hi | (sA_d + kc * ((8 * 2 * kGranuleBytes) >> 4));
+                const uint64_t db0 = db_hi | (sW_d + stage * (kStage >> 4));
                 if (elect_one()) {
-#ifdef SDF_CLOCKS
-                  if (!(p.flags & FL_DBG_NO_MMA))
-#endif
-                  {
-                    if (st.k16 == (PAIR ? 8 : 4)) {
 #pragma unroll
-                      for (int k = 0; k < (PAIR ? 8 : 4); ++k)
-                        umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
-                                       (kc | k) != 0 ? 1u : 0u);
-                    } else {
-                      for (int k = 0; k < st.k16; ++k)
-                        umma_any<PAIR>(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
-                                       (kc | k) != 0 ? 1u : 0u);
-                    }
-                  }
-                  if (PAIR) umma_commit2(&w_empty[stage], 3); else umma_commit(&w_empty[stage]);
-                  if (kc + 1 == st.kchunks) {
-                    if (PAIR) umma_commit2(&B.acc_full[g], 3); else umma_commit(&B.acc_full[g]);
-                  }
+                  for (int k = 0; k < 8; ++k)
+                    umma_f16_ss2(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                                 (kc | k) != 0 ? 1u : 0u);
+                  umma_commit2_u32(wempty_u + 8 * stage, 3);
+                  if (kc == 3) umma_commit2_u32(accfull_u + 8 * g, 3);
                 }
                 __syncwarp();
-                if (++stage == NST) { stage = 0; ++round; }
+                if (++stage == NST) { stage = 0; wpar ^= 1; }
               }
             }
             ++n0;
-#ifdef SDF_CLOCKS
-            ++c_steps;
-#endif
+            continue;
           }
+          for (int g = 0; g < n_groups; ++g) {
+            const uint32_t tmem_d = tmem_base + g * ng;
+            uint32_t a_d = sA_d;
+            int a_left = a_chunks;
+            int q = 0, q_left = 0;
+            for (int kc = 0; kc < kchunks; ++kc) {
+              if (g == 0) {
+                if (k_lo == 0) {
+                  if (kc == 0) {
+                    for (int j = 0; j < 4; ++j) mbar_wait_cluster_vote_u32(aq_u + 8 * j, par, poller);
+                    tc_fence_after();
+                  }
+                } else if (q < 4 && q_left == 0) {
+                  mbar_wait_cluster_vote_u32(aq_u + 8 * q, par, poller);
+                  tc_fence_after();
+                  ++q;
+                  q_left = k_lo;
+                }
+                --q_left;
+              }
+              mbar_wait_vote_u32(wfull_u + 8 * stage, wpar, poller);
+              mbar_wait_cluster_vote_u32(pfull_u + 8 * stage, wpar, poller);
+              tc_fence_after();
+              const uint64_t da0 = da_hi | a_d;
+              const uint64_t db0 = db_hi | (sW_d + stage * (kStage >> 4));
+              if (elect_one()) {
+                for (int k = 0; k < k16; ++k)
+                  umma_f16_ss2(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
+                               (kc | k) != 0 ? 1u : 0u);
+                umma_commit2_u32(wempty_u + 8 * stage, 3);
+                if (kc + 1 == kchunks) umma_commit2_u32(accfull_u + 8 * g, 3);
+              }
+              __syncwarp();
+              a_d += a_chunk_d;
+              if (--a_left == 0) { a_d = sA_d; a_left = a_chunks; }
+              if (++stage == NST) { stage = 0; wpar ^= 1; }
+            }
+          }
+          ++n0;
         }
-#ifdef SDF_CLOCKS
-        c_tot = clock64() - c_begin;
-        if (p.dbg_clk && lane == 0) {
-          unsigned long long* d = reinterpret_cast<unsigned long long*>(p.dbg_clk) + 64;
-          atomicAdd(d + 0, static_cast<unsigned long long>(c_alo));
-          atomicAdd(d + 1, static_cast<unsigned long long>(c_ahi));
-          atomicAdd(d + 2, static_cast<unsigned long long>(c_w));
-          atomicAdd(d + 3, static_cast<unsigned long long>(c_tot));
-          atomicAdd(d + 4, static_cast<unsigned long long>(c_steps));
-        }
-#endif
       }
     }
   } else {

@@ -327,4 +327,28 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// warp-uniform forms on shared-memory addresses, acquire at cluster scope (barriers the peer CTA arrives on)
+__device__ __forceinline__ void mbar_wait_cluster_vote_u32(uint32_t bar_addr, uint32_t parity, bool poller) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok = 0;
+    if (poller) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+    }
+    if (__any_sync(0xffffffffu, ok != 0)) break;
+    if (++spins > SDF_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void umma_commit2_u32(uint32_t bar_addr, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
+               "h"(cta_mask)
+               : "memory");
+}
+
 }  // namespace sdf

@@ -1,0 +1,9 @@
+for rep in 1 2; do
+for pr in 0 1; do
+  if [ $pr = 1 ]; then export SDFNET_PAIR=1; else unset SDFNET_PAIR; fi
+  g=$(python tools/grid_probe.py 384 2>&1 | grep -o "[0-9.]* Mq/s")
+  out=$(python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-grid 2>/dev/null)
+  b=$(echo "$out" | grep -o '"ms_per_step": [0-9.]*' | head -1)
+  k=$(echo "$out" | grep -o '"kernel_ms_per_step": {[^}]*}')
+  echo "PAIR=$pr rep$rep: grid $g | $b | $k"
+done; done
