@@ -614,6 +614,16 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
   }
 }
 
+// Spill-image store.  Images that are next read by a later kernel (q, adot, Zbar) are written with the streaming
+// (evict-first) policy so they do not push the lines this kernel still needs (prefetched operands, weights) out of L2.
+#ifndef SDF_STCS
+#define SDF_STCS 0  // (A/B on B200: no measurable difference)
+#endif
+template <int EPI>
+__device__ __forceinline__ void store_spill(uint8_t* ptr, const uint4& v) {
+  if (SDF_STCS && EPI != EPI_FWD_HIDDEN) __stcs(reinterpret_cast<uint4*>(ptr), v);
+  else *reinterpret_cast<uint4*>(ptr) = v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // Hidden-layer epilogue, overlapped form (fast mode, H = 512: two accumulator halves of 256 columns).
@@ -734,8 +744,8 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
       const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       if (io.out) {
-        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = p0;
-        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = p1;
+        store_spill<EPI>(io.out + img_off(c, e.prow), p0);
+        store_spill<EPI>(io.out + img_off(c + 8, e.prow), p1);
       }
       if (half == 0) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
@@ -871,8 +881,8 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       }
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
       if (io.out) {
-        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = pq[0];
-        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = pq[1];
+        store_spill<EPI>(io.out + img_off(c, e.prow), pq[0]);
+        store_spill<EPI>(io.out + img_off(c + 8, e.prow), pq[1]);
       }
       if (half == 0) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
