@@ -111,7 +111,7 @@ class ImplicitNet(nn.Module):
         dims = [d_in] + hidden + [1]
         self.num_layers = len(dims)
         self.skip_in = skip_in
-        print("skip_in", skip_in)  # reference model/networks.py:50
+        # (the reference prints skip_in here, model/networks.py:50; a drop-in keeps stdout clean for its callers)
         self.lipsitch = lipsitch
         self.d_in = d_in
         self.beta = beta
