@@ -59,6 +59,11 @@ namespace sdf {
 #ifndef SDF_COPY_SPLIT
 #define SDF_COPY_SPLIT 1
 #endif
+// reverse sweep: request the step's activation-image lines into L2 at the start of the step (ncu: almost all of them
+// come from DRAM - 6.7 GB read per 1M points - although the forward sweep of the same tile wrote them moments earlier)
+#ifndef SDF_L2PF_REV
+#define SDF_L2PF_REV 0  // (A/B: 3-5 % slower for the reverse sweep, twice)
+#endif
 #ifndef SDF_PF_NEXT
 #define SDF_PF_NEXT 0  // (requesting the next step's images one step ahead measured 18 % slower: L2 thrash)
 #endif
@@ -799,7 +804,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #ifndef SDF_NO_L2PF
   // (same-session A/B on B200: +3 % for the tangent / adjoint sweeps, whose operands come from HBM; -2 % for the
   // reverse sweep, whose activation images were written moments earlier and are mostly still in L2)
-  if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) {
+  if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN || (EPI == EPI_REV_HIDDEN && SDF_L2PF_REV)) {
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
