@@ -115,6 +115,14 @@ int sdfnet_mc_classify(const float* sdf, int32_t nx, int32_t ny, int32_t nz, uin
  * the index buffer exactly), otherwise writes their flat indices in ascending order. */
 int sdfnet_mc_compact(const uint8_t* case_index, int64_t n_cells, int64_t* active_cells, int64_t* n_active, void* stream);
 
+/* executor/executor.py:388 marching_cubes(sdf, level=0.0, spacing=spacing) -- vertex interpolation stage for the active
+ * cells: for cell c and edge e (Lorensen-Cline numbering: 0-3 bottom ring, 4-7 top ring, 8-11 verticals) whose corner
+ * signs differ, verts[(c*12+e)*3..] = (idx_a + t (idx_b - idx_a)) * spacing with t = f_a / (f_a - f_b) (index space times
+ * spacing, as skimage); non-crossing edges get (0,0,0).  edge_mask[c] has bit e set for crossing edges.  spacing3 is a
+ * HOST pointer to 3 floats.  The triangle tables of skimage's Lewiner variant are not restated (parity unpinned there). */
+int sdfnet_mc_edge_vertices(const float* sdf, int32_t nx, int32_t ny, int32_t nz, const int64_t* active_cells, int64_t n_active,
+                            const float* spacing3, float* verts, uint16_t* edge_mask, void* stream);
+
 /* Instrumentation (no reference counterpart; used by bench.py): kernels launched through this handle so far, and
  * CUDA-event timing of each kernel class on its launch stream.  Classes: 0 = layer chain forward (+ reverse),
  * 1 = layer chain tangent + adjoint, 2 = weight-gradient GEMM, 3 = everything else.  sdfnet_profile_read waits for the

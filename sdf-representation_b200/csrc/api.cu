@@ -36,6 +36,8 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n,
                         int step, cudaStream_t stream);
 cudaError_t launch_octree_flags(const float* sdf, int64_t n, float thresh, uint8_t* flags, cudaStream_t stream);
 cudaError_t launch_mc_classify(const float* sdf, int nx, int ny, int nz, uint8_t* cases, cudaStream_t stream);
+cudaError_t launch_mc_edge_vertices(const float* sdf, int nx, int ny, int nz, const long* cells, long n_cells, float sx, float sy, float sz,
+                                    float* verts, unsigned short* mask, cudaStream_t stream);
 long compact_num_blocks(long n);
 cudaError_t launch_count_flags(const uint8_t* v, long n, int mode, long* total, long* scratch, cudaStream_t stream);
 cudaError_t launch_compact(const uint8_t* v, long n, int mode, const uint64_t* keys, long* out_idx, uint64_t* out_keys,
@@ -836,6 +838,16 @@ extern "C" int sdfnet_mc_classify(const float* sdf, int32_t nx, int32_t ny, int3
     const int64_t total = static_cast<int64_t>(nx - 1) * (ny - 1) * (nz - 1);
     return sdfnet_mc_compact(case_index, total, active_cells, n_active, stream_);
   }
+  return 0;
+}
+
+extern "C" int sdfnet_mc_edge_vertices(const float* sdf, int32_t nx, int32_t ny, int32_t nz, const int64_t* active_cells, int64_t n_active,
+                                       const float* spacing3, float* verts, uint16_t* edge_mask, void* stream_) {
+  if (!sdf || !spacing3 || (n_active > 0 && (!active_cells || !verts || !edge_mask))) return fail(1, "sdfnet_mc_edge_vertices: null argument");
+  if (nx < 2 || ny < 2 || nz < 2 || n_active < 0) return fail(1, "sdfnet_mc_edge_vertices: bad sizes");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CU(launch_mc_edge_vertices(sdf, nx, ny, nz, reinterpret_cast<const long*>(active_cells), n_active, spacing3[0], spacing3[1], spacing3[2],
+                             verts, edge_mask, stream));
   return 0;
 }
 

@@ -449,6 +449,64 @@ __global__ void mc_classify_kernel(const float* __restrict__ sdf, int nx, int ny
   }
 }
 
+// Edge vertices of the active cells (the interpolation stage of marching cubes, level 0).  One thread per (cell, edge);
+// edge e of a cell joins corners kEdgeA[e], kEdgeB[e] (Lorensen-Cline numbering, as the corner order above).  A crossing
+// edge (corner signs differ) gets t = f_a / (f_a - f_b) and the point (idx_a + t (idx_b - idx_a)) * spacing -- index space
+// times spacing, the convention of skimage.measure.marching_cubes(volume, 0.0, spacing=...) at the reference call site.
+// Every operation is a single correctly rounded fp32 operation (no contraction), so the oracle reproduces the bits.
+__constant__ int kEdgeA[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
+__constant__ int kEdgeB[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+__constant__ int kCornerD[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+__global__ void mc_edge_vertices_kernel(const float* __restrict__ sdf, int nx, int ny, int nz, const long* __restrict__ cells, long n_cells,
+                                        float sx, float sy, float sz, float* __restrict__ verts, unsigned short* __restrict__ mask) {
+  const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long ci = t / 12;
+  const int e = static_cast<int>(t - ci * 12);
+  if (ci >= n_cells) return;
+  const long cell = cells[ci];
+  const int cy = ny - 1, cz = nz - 1;
+  const int k = static_cast<int>(cell % cz);
+  const int j = static_cast<int>((cell / cz) % cy);
+  const int i = static_cast<int>(cell / (static_cast<long>(cz) * cy));
+  const int a = kEdgeA[e], b = kEdgeB[e];
+  const int ia[3] = {i + kCornerD[a][0], j + kCornerD[a][1], k + kCornerD[a][2]};
+  const int ib[3] = {i + kCornerD[b][0], j + kCornerD[b][1], k + kCornerD[b][2]};
+  const float fa = __ldg(sdf + (static_cast<long>(ia[0]) * ny + ia[1]) * nz + ia[2]);
+  const float fb = __ldg(sdf + (static_cast<long>(ib[0]) * ny + ib[1]) * nz + ib[2]);
+  const bool cross = (fa < 0.f) != (fb < 0.f);
+  float v[3] = {0.f, 0.f, 0.f};
+  if (cross) {
+    const float tt = __fdiv_rn(fa, __fsub_rn(fa, fb));
+    const float sp[3] = {sx, sy, sz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float pa = static_cast<float>(ia[d]), pb = static_cast<float>(ib[d]);
+      v[d] = __fmul_rn(__fadd_rn(pa, __fmul_rn(tt, __fsub_rn(pb, pa))), sp[d]);
+    }
+  }
+  float* o = verts + t * 3;
+  o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+  if (e == 0) {
+    // 12-bit mask of the crossing edges of the cell = edges whose corner bits differ in the 8-bit corner sign mask
+    unsigned neg = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      neg |= (__ldg(sdf + (static_cast<long>(i + kCornerD[c][0]) * ny + j + kCornerD[c][1]) * nz + k + kCornerD[c][2]) < 0.f ? 1u : 0u) << c;
+    unsigned m = 0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) m |= (((neg >> kEdgeA[q]) ^ (neg >> kEdgeB[q])) & 1u) << q;
+    mask[ci] = static_cast<unsigned short>(m);
+  }
+}
+cudaError_t launch_mc_edge_vertices(const float* sdf, int nx, int ny, int nz, const long* cells, long n_cells, float sx, float sy, float sz,
+                                    float* verts, unsigned short* mask, cudaStream_t stream) {
+  if (n_cells <= 0) return cudaSuccess;
+  const long threads = n_cells * 12;
+  const long blocks = (threads + 383) / 384;  // 384 = 32 cells per block
+  mc_edge_vertices_kernel<<<static_cast<unsigned>(blocks), 384, 0, stream>>>(sdf, nx, ny, nz, cells, n_cells, sx, sy, sz, verts, mask);
+  return cudaGetLastError();
+}
+
 // Ordered compaction in three passes: per-block counts, scan of the block counts (one block), scatter.
 constexpr int kScanBlock = 1024;
 constexpr int kItemsPerThread = 4;

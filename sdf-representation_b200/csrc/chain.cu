@@ -64,6 +64,9 @@ namespace sdf {
 #ifndef SDF_L2PF_REV
 #define SDF_L2PF_REV 0  // (A/B: 3-5 % slower for the reverse sweep, twice)
 #endif
+#ifndef SDF_PACKED_ALL
+#define SDF_PACKED_ALL 0
+#endif
 #ifndef SDF_PF_NEXT
 #define SDF_PF_NEXT 0  // (requesting the next step's images one step ahead measured 18 % slower: L2 thrash)
 #endif
@@ -494,6 +497,11 @@ struct P2<DT_FP16> {
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
   }
+  static __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  }
   static __device__ __forceinline__ uint32_t max(uint32_t a, uint32_t b) {
     uint32_t d;
     asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
@@ -525,6 +533,11 @@ struct P2<DT_BF16> {
   static __device__ __forceinline__ uint32_t fma(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+  }
+  static __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
   }
   static __device__ __forceinline__ uint32_t max(uint32_t a, uint32_t b) {
@@ -564,6 +577,26 @@ __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& 
     }
   } else {
     uint32_t uo[4];
+#if SDF_PACKED_ALL
+    // everything on packed pairs: the accumulator pair is rounded to 16 bits first (the result is stored in 16 bits
+    // anyway), then one packed multiply-add per term
+    const uint32_t one2 = H16<DT>::pack(1.f, 1.f), beta2 = H16<DT>::pack(k.beta, k.beta);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t e2 = P2<DT>::ex2(P2<DT>::mul(word(xa, i), nbl2_2));  // exp(-beta a) = 1 - act'(z)
+      const uint32_t vh = H16<DT>::pack(v[2 * i], v[2 * i + 1]);
+      if (EPI == EPI_REV_HIDDEN) {
+        o[i] = P2<DT>::mul(vh, P2<DT>::sub(one2, e2));
+      } else if (EPI == EPI_TAN_HIDDEN) {
+        const uint32_t wh = P2<DT>::mul(vh, e2);                 // (1 - s') zdot
+        o[i] = P2<DT>::sub(vh, wh);                              // adot = s' zdot
+        uo[i] = P2<DT>::mul(P2<DT>::mul(wh, beta2), word(xb, i));  // u = beta (1 - s') zdot q
+      } else {  // EPI_ADJ_HIDDEN
+        const uint32_t sp = P2<DT>::sub(one2, e2);
+        o[i] = has_b ? P2<DT>::fma(vh, sp, word(xb, i)) : P2<DT>::mul(vh, sp);  // s' r + u
+      }
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 ef = H16<DT>::unpack(P2<DT>::ex2(P2<DT>::mul(word(xa, i), nbl2_2)));  // exp(-beta a) = 1 - act'(z)
@@ -579,6 +612,7 @@ __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& 
         if (has_b) o[i] = P2<DT>::add(o[i], word(xb, i));       // + u
       }
     }
+#endif
     if (EPI == EPI_TAN_HIDDEN) *ou = make_uint4(uo[0], uo[1], uo[2], uo[3]);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);

@@ -85,6 +85,31 @@ def mc_classify(sdf_block, compact=True):
     return cases, active
 
 
+@torch.no_grad()
+def mc_edge_vertices(sdf_block, active, spacing=(1.0, 1.0, 1.0)):
+    """Vertex-interpolation stage of ``marching_cubes(sdf, level=0.0, spacing=spacing)`` (executor/executor.py:388) for
+    the active cells of ``mc_classify``: returns (verts float32 [n_active, 12, 3], edge_mask int16 [n_active]); edge e of
+    a cell (Lorensen-Cline numbering) carries the level-0 crossing point in index space times ``spacing`` when its bit
+    in the mask is set, (0, 0, 0) otherwise.  The grid stays on the device; no CPU fallback."""
+    lib = _lib.load()
+    if not sdf_block.is_cuda or sdf_block.dtype != torch.float32 or sdf_block.dim() != 3:
+        raise RuntimeError("mc_edge_vertices needs a float32 CUDA block [nx, ny, nz] (no CPU fallback)")
+    if not active.is_cuda or active.dtype != torch.int64:
+        raise RuntimeError("mc_edge_vertices needs the int64 CUDA active-cell list of mc_classify")
+    sdf_block = sdf_block.contiguous()
+    active = active.contiguous()
+    nx, ny, nz = sdf_block.shape
+    dev = sdf_block.device
+    n = active.numel()
+    verts = torch.empty((n, 12, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((n,), dtype=torch.int16, device=dev)
+    sp = (ctypes.c_float * 3)(*[float(v) for v in spacing])
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfnet_mc_edge_vertices(_ptr(sdf_block), nx, ny, nz, _ptr(active), n, ctypes.cast(sp, ctypes.c_void_p),
+                                               _ptr(verts), _ptr(mask), _stream(dev)), "sdfnet_mc_edge_vertices")
+    return verts, mask
+
+
 # ---------------------------------------------------------------------------------------------- octree
 def octree_children(keys, flags):
     """Morton keys of the 8 children of every flagged cell, in order (device-side ordered compaction)."""

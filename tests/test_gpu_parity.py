@@ -458,6 +458,26 @@ def test_mc_classify_bit_exact():
     assert 0 < ra.size < rc.size
 
 
+def test_mc_edge_vertices_bit_exact():
+    """Vertex interpolation of the active cells == oracle, bit for bit, given the GPU's own SDF block."""
+    from sdf_representation_b200 import inference
+
+    d = load_golden("softplus_skip_128x4.npz")
+    net = make_net(d, "fast")
+    n = 33
+    vol = inference.grid_sdf(net, n)
+    _, active = inference.mc_classify(vol)
+    spacing = (2.0 / (n - 1), 2.0 / (n - 1), 0.25)
+    verts, mask = inference.mc_edge_vertices(vol, active, spacing)
+    rv, rm = orc.mc_edge_vertices(vol.cpu().numpy(), active.cpu().numpy(), spacing)
+    assert np.array_equal(mask.cpu().numpy().view(np.uint16), rm)
+    assert np.array_equal(verts.cpu().numpy().view(np.uint32), rv.view(np.uint32))
+    assert (rm != 0).all()  # every active cell has at least one crossing edge
+    # empty list: no launch, empty outputs
+    v0, m0 = inference.mc_edge_vertices(vol, active[:0], spacing)
+    assert v0.shape == (0, 12, 3) and m0.shape == (0,)
+
+
 def test_adam_step_matches_torch():
     from sdf_representation_b200 import engine
 

@@ -91,6 +91,35 @@ def test_mc_cases_sphere():
     assert 0 < active.size < flat.size
 
 
+def test_mc_edge_vertices_sphere():
+    """The interpolated edge points of a sphere's active cells lie on the sphere (to the linear-interpolation error)."""
+    n = 24
+    ax = np.linspace(-1, 1, n, dtype=np.float32)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    sdf = (np.sqrt(X * X + Y * Y + Z * Z) - np.float32(0.6)).astype(np.float32)
+    _, active = orc.mc_cases(sdf)
+    h = 2.0 / (n - 1)
+    verts, mask = orc.mc_edge_vertices(sdf, active, (h, h, h))
+    assert verts.shape == (active.size, 12, 3) and mask.dtype == np.uint16
+    assert (mask != 0).all()
+    on = ((mask[:, None] >> np.arange(12)[None, :]) & 1).astype(bool)
+    p = verts[on] - 1.0  # index space * spacing has its origin at the (-1,-1,-1) corner
+    r = np.sqrt((p * p).sum(-1))
+    assert np.abs(r - 0.6).max() < 0.5 * h * h / 0.6 + 1e-5
+    assert (verts[~on] == 0).all()
+    # one cell by hand
+    c = int(active[len(active) // 2])
+    k, j, i = c % (n - 1), (c // (n - 1)) % (n - 1), c // ((n - 1) * (n - 1))
+    for e, (a, b) in enumerate(orc._MC_EDGES):
+        ia = np.array([i, j, k]) + np.array(orc._MC_CORNERS[a])
+        ib = np.array([i, j, k]) + np.array(orc._MC_CORNERS[b])
+        fa, fb = sdf[tuple(ia)], sdf[tuple(ib)]
+        if (fa < 0) != (fb < 0):
+            t = np.float32(fa / np.float32(fa - fb))
+            want = (ia.astype(np.float32) + t * (ib - ia).astype(np.float32)) * np.float32(h)
+            assert np.allclose(verts[len(active) // 2, e], want, rtol=0, atol=1e-6)
+
+
 def test_octree_keys_and_refinement():
     lv = orc.octree_build(lambda c: np.sqrt((c * c).sum(-1)) - np.float32(0.5), 5, 2, np.sqrt(3.0) / 2)
     assert [len(l["keys"]) for l in lv[:3]] == [1, 8, 64]
