@@ -88,7 +88,11 @@ struct sdfnet_handle {
   sdfnet_desc d;
   int H, L, skip, num_sms;
   bool relu, parity;
-  bool pair;               // fast mode, H = 512: the chain kernel runs on CTA pairs (tcgen05 cta_group::2)
+  // fast mode, H = 512: the chain kernel can run on CTA pairs (tcgen05 cta_group::2, second packed-weight layout Fp / Rp).
+  // pair_train: training programs (forward + reverse with spills, tangent + adjoint) use it -- measured 2 % faster per
+  // step than single CTAs (tan+adj -4 %); pair_infer: forward-only programs too (measured 3 % slower, off by default).
+  // SDFNET_PAIR=0 disables both, SDFNET_PAIR=1 enables both.
+  bool pair_train, pair_infer;
   int pts;                 // points per tile: 128 (fast) or 64 (parity)
   float* scale_dev = nullptr;      // [0] seed multiplier (power of two), [1] its inverse
   unsigned* absmax_dev = nullptr;  // running max |seed| of the current chunk
@@ -96,7 +100,15 @@ struct sdfnet_handle {
   size_t wpack_bytes = 0;
   float* bias = nullptr;
   float* w_last = nullptr;
-  std::vector<StepImage> F, R;  // F[0..L], R[0..L-1]
+  std::vector<StepImage> F, R;    // F[0..L], R[0..L-1]: single-CTA layout
+  std::vector<StepImage> Fp, Rp;  // CTA-pair layout (only when pair_train || pair_infer)
+  // Each layout is packed when sdfnet_pack_weights is called only if a program has used it before; a layout that is
+  // first needed later is packed on demand from the parameter pointers of the last sdfnet_pack_weights call (the
+  // caller packs right before launching, so they are current).  Training then packs the pair layout only, inference
+  // the single-CTA layout only.
+  std::vector<const float*> Wptr;
+  bool layout_used[2] = {false, false};
+  bool layout_ok[2] = {false, false};
   // gradient accumulators
   float* acc = nullptr;
   size_t acc_floats = 0;
@@ -186,20 +198,29 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   h->relu = desc->beta == 0.f;
   h->parity = desc->precision == 1;
   h->pts = h->parity ? kParityPoints : kTileRows;
-  // CTA-pair layer chain (cta_group::2): functional and tested, but on B200 the cluster hand-shakes cost more than the
-  // halved weight traffic gains: opt-in with SDFNET_PAIR=1
-  h->pair = !h->parity && desc->hidden == 512 && getenv("SDFNET_PAIR") != nullptr;
+  // CTA-pair layer chain (cta_group::2): halves the L2 -> SM weight bytes and doubles the time-depth of the weight ring
+  // 
+  {
+    const char* e = getenv("SDFNET_PAIR");
+    const bool can = !h->parity && desc->hidden == 512;
+    h->pair_train = can && !(e && e[0] == '0');
+    h->pair_infer = can && e && e[0] == '1';
+  }
   h->num_sms = prop.multiProcessorCount;
   const int H = h->H, L = h->L;
   uint32_t off = 0;
-  h->F.resize(L + 1);
-  h->R.resize(L);
   const bool sp = h->parity;
-  h->F[0] = make_image(H, 1, 1, false, off);                  // K = 16 (input block, already split along K)
-  for (int l = 1; l < L; ++l) h->F[l] = make_image(H, H / 16, h->pair ? 8 : 4, sp, off);
-  h->F[L] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (row 0 = lin_L)
-  for (int l = L - 1; l >= 1; --l) h->R[l] = make_image(H, H / 16, h->pair ? 8 : 4, sp, off);
-  h->R[0] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (rows 0..2 = d/dx)
+  auto build = [&](std::vector<StepImage>& F, std::vector<StepImage>& R, int k16_hidden) {
+    F.resize(L + 1);
+    R.resize(L);
+    F[0] = make_image(H, 1, 1, false, off);                  // K = 16 (input block, already split along K)
+    for (int l = 1; l < L; ++l) F[l] = make_image(H, H / 16, k16_hidden, sp, off);
+    F[L] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (row 0 = lin_L)
+    for (int l = L - 1; l >= 1; --l) R[l] = make_image(H, H / 16, k16_hidden, sp, off);
+    R[0] = make_image(16, H / 16, H / 16, sp, off);          // N = 16 (rows 0..2 = d/dx)
+  };
+  build(h->F, h->R, 4);
+  if (h->pair_train || h->pair_infer) build(h->Fp, h->Rp, 8);
   h->wpack_bytes = off;
   CU(cudaMalloc(&h->wpack, h->wpack_bytes));
   CU(cudaMalloc(&h->bias, sizeof(float) * (L + 1) * H));
@@ -261,26 +282,59 @@ static int out_dim_of(const sdfnet_handle* h, int l) {
   return (h->skip > 0 && l + 1 == h->skip) ? h->H - 3 : h->H;
 }
 
-extern "C" int sdfnet_pack_weights(sdfnet_t h, const float* const* W, const float* const* b, void* stream_) {
-  if (!h || !W || !b) return fail(1, "sdfnet_pack_weights: null argument");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// pack one weight layout (0 = single CTA, 1 = CTA pair) from the parameter pointers of the last sdfnet_pack_weights call
+static int pack_layout(sdfnet_t h, int layout, cudaStream_t stream) {
   const int H = h->H, L = h->L, dt = h->d.dtype;
   const float c = static_cast<float>(1.0 / std::sqrt(2.0));
-  Launch lp(h, PC_OTHER, stream, 3 * (L + 1));
+  const std::vector<StepImage>& F = layout ? h->Fp : h->F;
+  const std::vector<StepImage>& R = layout ? h->Rp : h->R;
+  const int split_ctas = layout ? 2 : 1;
+  const float* const* W = h->Wptr.data();
+  Launch lp(h, PC_OTHER, stream, 2 * L + 1);
   for (int l = 0; l <= L; ++l) {
-    if (!W[l] || !b[l]) return fail(1, "sdfnet_pack_weights: null parameter pointer for layer %d", l);
-    const StepImage& s = h->F[l];
+    const StepImage& s = F[l];
     const int kind = l == 0 ? PK_F0 : (l == L ? PK_FL : PK_FH);
     const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
     CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           kind, scale, dt, s.split, h->pair ? 2 : 1, stream));
-    CU(launch_pack_bias(b[l], out_dim_of(h, l), h->bias + static_cast<size_t>(l) * H, H, stream));
+                           kind, scale, dt, s.split, split_ctas, stream));
   }
   for (int l = L - 1; l >= 0; --l) {
-    const StepImage& s = h->R[l];
+    const StepImage& s = R[l];
     const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
     CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           l == 0 ? PK_R0 : PK_RH, scale, dt, s.split, h->pair ? 2 : 1, stream));
+                           l == 0 ? PK_R0 : PK_RH, scale, dt, s.split, split_ctas, stream));
+  }
+  h->layout_ok[layout] = true;
+  return 0;
+}
+// called by every chain launch site: the layout its program was built on must hold the current weights
+static int ensure_layout(sdfnet_t h, bool pr, cudaStream_t stream) {
+  const int layout = pr ? 1 : 0;
+  h->layout_used[layout] = true;
+  if (h->layout_ok[layout]) return 0;
+  if (h->Wptr.empty()) return fail(1, "sdfnet: sdfnet_pack_weights has not been called");
+  return pack_layout(h, layout, stream);
+}
+
+extern "C" int sdfnet_pack_weights(sdfnet_t h, const float* const* W, const float* const* b, void* stream_) {
+  if (!h || !W || !b) return fail(1, "sdfnet_pack_weights: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int H = h->H, L = h->L;
+  const bool both = !h->Fp.empty();
+  for (int l = 0; l <= L; ++l)
+    if (!W[l] || !b[l]) return fail(1, "sdfnet_pack_weights: null parameter pointer for layer %d", l);
+  {
+    Launch lp(h, PC_OTHER, stream, L + 1);
+    for (int l = 0; l <= L; ++l) CU(launch_pack_bias(b[l], out_dim_of(h, l), h->bias + static_cast<size_t>(l) * H, H, stream));
+  }
+  h->Wptr.assign(W, W + L + 1);
+  for (int layout = 0; layout < 2; ++layout) {
+    h->layout_ok[layout] = false;
+    if (layout == 1 && !both) continue;
+    if (h->layout_used[layout]) {
+      const int rc = pack_layout(h, layout, stream);
+      if (rc) return rc;
+    }
   }
   CU(cudaMemcpyAsync(h->w_last, W[L], sizeof(float) * H, cudaMemcpyDeviceToDevice, stream));
   return 0;
@@ -318,21 +372,26 @@ static void base_params(const sdfnet_handle* h, ChainParams& p) {
   static const uint32_t dbg = [] { const char* e = getenv("SDFNET_DEBUG_FLAGS"); return e ? static_cast<uint32_t>(strtoul(e, nullptr, 0)) : 0u; }();
   p.flags |= dbg & 0xffff0000u;
 }
-static void prog_forward(const sdfnet_handle* h, ChainParams& p) {
-  for (int l = 0; l < h->L; ++l) add_step(p, EPI_FWD_HIDDEN, l, &h->F[l]);
-  add_step(p, EPI_FWD_LAST, h->L, &h->F[h->L]);
+// pr: build the program on the CTA-pair weight layout (the launch must then use the pair kernel)
+static void prog_forward(const sdfnet_handle* h, ChainParams& p, bool pr) {
+  const std::vector<StepImage>& F = pr ? h->Fp : h->F;
+  for (int l = 0; l < h->L; ++l) add_step(p, EPI_FWD_HIDDEN, l, &F[l]);
+  add_step(p, EPI_FWD_LAST, h->L, &F[h->L]);
 }
-static void prog_reverse(const sdfnet_handle* h, ChainParams& p) {
+static void prog_reverse(const sdfnet_handle* h, ChainParams& p, bool pr) {
+  const std::vector<StepImage>& R = pr ? h->Rp : h->R;
   add_step(p, EPI_REV_START, h->L - 1, nullptr);
-  for (int l = h->L - 1; l >= 1; --l) add_step(p, EPI_REV_HIDDEN, l, &h->R[l]);
-  add_step(p, EPI_REV_LAST, 0, &h->R[0]);
+  for (int l = h->L - 1; l >= 1; --l) add_step(p, EPI_REV_HIDDEN, l, &R[l]);
+  add_step(p, EPI_REV_LAST, 0, &R[0]);
 }
-static void prog_tangent(const sdfnet_handle* h, ChainParams& p) {
-  for (int l = 0; l < h->L; ++l) add_step(p, EPI_TAN_HIDDEN, l, &h->F[l]);
+static void prog_tangent(const sdfnet_handle* h, ChainParams& p, bool pr) {
+  const std::vector<StepImage>& F = pr ? h->Fp : h->F;
+  for (int l = 0; l < h->L; ++l) add_step(p, EPI_TAN_HIDDEN, l, &F[l]);
 }
-static void prog_adjoint(const sdfnet_handle* h, ChainParams& p) {
+static void prog_adjoint(const sdfnet_handle* h, ChainParams& p, bool pr) {
+  const std::vector<StepImage>& R = pr ? h->Rp : h->R;
   add_step(p, EPI_ADJ_START, h->L - 1, nullptr);
-  for (int l = h->L - 2; l >= 0; --l) add_step(p, EPI_ADJ_HIDDEN, l, &h->R[l + 1]);
+  for (int l = h->L - 2; l >= 0; --l) add_step(p, EPI_ADJ_HIDDEN, l, &R[l + 1]);
 }
 
 // workspace carving -------------------------------------------------------------------------------
@@ -392,10 +451,11 @@ static int run_forward(sdfnet_t h, ChainParams& p, int64_t n, cudaStream_t strea
   p.n = n;
   p.n_tiles = static_cast<int>((n + h->pts - 1) / h->pts);
   p.tile_stride = (p.n_tiles + 1) & ~1;
-  prog_forward(h, p);
+  if (int rc = ensure_layout(h, h->pair_infer, stream)) return rc;
+  prog_forward(h, p, h->pair_infer);
   finish_program(p);
   Launch lr(h, PC_CHAIN_FG, stream);
-  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, stream));
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair_infer ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 
@@ -484,11 +544,12 @@ extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float*
     carve(h, 0, ws, p.n_tiles, s);
     p.Aimg = s.A;
     p.flags |= FL_SPILL_A;
-    prog_forward(h, p);
-    prog_reverse(h, p);
+    if (int rc = ensure_layout(h, h->pair_infer, static_cast<cudaStream_t>(stream))) return rc;
+    prog_forward(h, p, h->pair_infer);
+    prog_reverse(h, p, h->pair_infer);
     finish_program(p);
     Launch lr(h, PC_CHAIN_FG, static_cast<cudaStream_t>(stream));
-    CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, static_cast<cudaStream_t>(stream)));
+    CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair_infer ? 1 : 0, h->num_sms, static_cast<cudaStream_t>(stream)));
   }
   return 0;
 }
@@ -635,11 +696,12 @@ int run_fg(sdfnet_t h, const float* x, int64_t m, const Spill& s, bool need_g, c
   p.g_out = need_g ? s.g : nullptr;
   p.Aimg = s.A; p.Qimg = s.Q; p.Ximg = s.X;
   p.flags |= FL_SPILL_A | FL_SPILL_X | (need_g ? FL_SPILL_Q : 0u);
-  prog_forward(h, p);
-  if (need_g) prog_reverse(h, p);
+  if (int rc = ensure_layout(h, h->pair_train, stream)) return rc;
+  prog_forward(h, p, h->pair_train);
+  if (need_g) prog_reverse(h, p, h->pair_train);
   finish_program(p);
   Launch lr(h, PC_CHAIN_FG, stream);
-  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, stream));
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair_train ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 // tangent (+adjoint) sweeps over one chunk
@@ -651,14 +713,15 @@ int run_ta(sdfnet_t h, int64_t m, const Spill& s, const float* fbar, const float
   p.tile_stride = (p.n_tiles + 1) & ~1;
   p.fbar = fbar; p.gbar = gbar; p.seed_mult = h->scale_dev;
   p.Aimg = s.A; p.Qimg = s.Q; p.ADimg = s.AD; p.Uimg = s.U; p.Zimg = s.Z; p.Ximg = s.X; p.Gimg = s.G; p.Simg = s.S;
+  if (int rc = ensure_layout(h, h->pair_train, stream)) return rc;
   if (gbar) {
     p.flags |= FL_TANGENT;
-    prog_tangent(h, p);
+    prog_tangent(h, p, h->pair_train);
   }
-  prog_adjoint(h, p);
+  prog_adjoint(h, p, h->pair_train);
   finish_program(p);
   Launch lr(h, PC_CHAIN_TA, stream);
-  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair ? 1 : 0, h->num_sms, stream));
+  CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair_train ? 1 : 0, h->num_sms, stream));
   return 0;
 }
 int64_t chunk_points(sdfnet_t h, size_t ws_bytes) {

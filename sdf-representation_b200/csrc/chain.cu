@@ -254,14 +254,13 @@ __device__ __forceinline__ void put_block(const Epi& e, int g, const uint4& v, b
 struct Bars {
   uint64_t* acc_full;  // [2]  MMA issuer -> epilogue: accumulator half g is complete
   uint64_t* a_q;       // [4]  epilogue -> MMA issuer: A-image columns [128 j, 128 j + 128) are in place
-  bool remote;         //      CTA pair, rank 1: the issuer's barriers live in the leader CTA
+  bool remote;         //      CTA pair, rank 1: a relay warp forwards the quarter barriers to the leader CTA
 };
 // One arrival per epilogue warp on quarter barrier j (every lane has fenced its own shared-memory / TMEM accesses).
 __device__ __forceinline__ void arrive_quarter(const Bars& B, int j) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
-    if (B.remote) mbar_arrive_cluster(&B.a_q[j], 0);
-    else mbar_arrive(&B.a_q[j]);
+    mbar_arrive(&B.a_q[j]);
   }
 }
 __device__ __forceinline__ void arrive_all_quarters(const Bars& B) {
@@ -269,8 +268,7 @@ __device__ __forceinline__ void arrive_all_quarters(const Bars& B) {
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (B.remote) mbar_arrive_cluster(&B.a_q[j], 0);
-      else mbar_arrive(&B.a_q[j]);
+      mbar_arrive(&B.a_q[j]);
     }
   }
 }
@@ -1003,8 +1001,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   uint64_t* peer_full = bars + 2 * NST;   // [NST] pair, leader only: the peer's half chunk has landed
   Bars B;
   B.acc_full = bars + 3 * NST;            // [2]
-  B.a_q = bars + 3 * NST + 2;             // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 6);
+  B.a_q = bars + 3 * NST + 2;             // [4]  this CTA's epilogue warps
+  uint64_t* a_qr = bars + 3 * NST + 6;    // [4]  pair, leader only: the peer CTA's quarter is in place (one relayed arrival)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 10);
   float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
@@ -1025,7 +1024,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     }
     mbar_init(&B.acc_full[0], 1);
     mbar_init(&B.acc_full[1], 1);
-    for (int j = 0; j < 4; ++j) mbar_init(&B.a_q[j], kEpiWarps * (PAIR ? 2 : 1));
+    for (int j = 0; j < 4; ++j) {
+      mbar_init(&B.a_q[j], kEpiWarps);
+      mbar_init(&a_qr[j], 1);
+    }
     mbar_fence_init();
   }
   if (warp == kMmaWarp) {
@@ -1219,6 +1221,26 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           ++n0;
         }
       }
+    } else if (PAIR && warp == kMmaWarp + 1 && rank != 0) {
+      // ------------------------------------------------------------------ peer CTA: quarter-barrier relay.  The peer's
+      // 16 epilogue warps arrive on their own CTA's barriers (a release.cluster arrive is a MEMBAR + ERRBAR in every
+      // warp: 10 % of the pair kernel's samples); this otherwise idle warp forwards each completed quarter to the
+      // leader with one remote arrival.
+      if (lane == 0) {
+        uint32_t n0 = 0;
+        for (int it = it0; it < it_end; it += it_step) {
+          for (int s = 0; s < p.n_steps; ++s) {
+            if (p.steps[s].n_groups == 0) continue;
+            for (int j = 0; j < 4; ++j) {
+              mbar_wait(&B.a_q[j], n0 & 1);
+              tc_fence_after();
+              tc_fence_before();
+              mbar_arrive_cluster(&a_qr[j], 0);
+            }
+            ++n0;
+          }
+        }
+      }
     } else if (warp == kMmaWarp) {
       // ------------------------------------------------------------------ MMA issuer, CTA pair (leader CTA), lean form
       // of the loop above: M = 256 MMAs over both CTAs' tiles, 8 per weight chunk (K = 128), so the issue cost per
@@ -1226,7 +1248,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       // tensor time.
       const uint32_t sA_d = smem_u32(sA) >> 4, sW_d = smem_u32(sW) >> 4;
       const uint32_t wfull_u = smem_u32(w_full), wempty_u = smem_u32(w_empty), pfull_u = smem_u32(peer_full);
-      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q);
+      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q), aqr_u = smem_u32(a_qr);
       uint32_t stage = 0, wpar = 0, n0 = 0;
       const bool poller = elect_one();
       for (int it = it0; it < it_end; it += it_step) {
@@ -1252,11 +1274,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                 if (g == 0) {
                   if (k_lo == 0) {
                     if (kc == 0) {
-                      for (int j = 0; j < 4; ++j) mbar_wait_cluster_vote_u32(aq_u + 8 * j, par, poller);
+                      for (int j = 0; j < 4; ++j) { mbar_wait_vote_u32(aq_u + 8 * j, par, poller); mbar_wait_cluster_vote_u32(aqr_u + 8 * j, par, poller); }
                       tc_fence_after();
                     }
                   } else {  // one weight chunk per 128-column quarter of the A images
-                    mbar_wait_cluster_vote_u32(aq_u + 8 * kc, par, poller);
+                    mbar_wait_vote_u32(aq_u + 8 * kc, par, poller);
+                    mbar_wait_cluster_vote_u32(aqr_u + 8 * kc, par, poller);
                     tc_fence_after();
                   }
                 }
@@ -1289,11 +1312,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               if (g == 0) {
                 if (k_lo == 0) {
                   if (kc == 0) {
-                    for (int j = 0; j < 4; ++j) mbar_wait_cluster_vote_u32(aq_u + 8 * j, par, poller);
+                    for (int j = 0; j < 4; ++j) { mbar_wait_vote_u32(aq_u + 8 * j, par, poller); mbar_wait_cluster_vote_u32(aqr_u + 8 * j, par, poller); }
                     tc_fence_after();
                   }
                 } else if (q < 4 && q_left == 0) {
-                  mbar_wait_cluster_vote_u32(aq_u + 8 * q, par, poller);
+                  mbar_wait_vote_u32(aq_u + 8 * q, par, poller);
+                  mbar_wait_cluster_vote_u32(aqr_u + 8 * q, par, poller);
                   tc_fence_after();
                   ++q;
                   q_left = k_lo;
@@ -1683,10 +1707,14 @@ static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t st
 cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int pair, int num_sms, cudaStream_t stream) {
   if (p.n_tiles <= 0) return cudaSuccess;
   if (parity) return dtype == DT_BF16 ? launch_one<DT_BF16, true, false>(p, num_sms, stream) : launch_one<DT_FP16, true, false>(p, num_sms, stream);
-  if (pair) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true>(p, num_sms, stream) : launch_one<DT_FP16, false, true>(p, num_sms, stream);
   // program family of this launch (api.cu builds forward [+ reverse] programs or tangent / adjoint programs)
   bool fr = false, ta = false;
   for (int s = 0; s < p.n_steps; ++s) (p.steps[s].epi <= EPI_REV_LAST ? fr : ta) = true;
+  if (pair) {
+    if (fr && !ta) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true, 1>(p, num_sms, stream) : launch_one<DT_FP16, false, true, 1>(p, num_sms, stream);
+    if (ta && !fr) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true, 2>(p, num_sms, stream) : launch_one<DT_FP16, false, true, 2>(p, num_sms, stream);
+    return dtype == DT_BF16 ? launch_one<DT_BF16, false, true, 3>(p, num_sms, stream) : launch_one<DT_FP16, false, true, 3>(p, num_sms, stream);
+  }
   if (fr && !ta) return dtype == DT_BF16 ? launch_one<DT_BF16, false, false, 1>(p, num_sms, stream) : launch_one<DT_FP16, false, false, 1>(p, num_sms, stream);
   if (ta && !fr) return dtype == DT_BF16 ? launch_one<DT_BF16, false, false, 2>(p, num_sms, stream) : launch_one<DT_FP16, false, false, 2>(p, num_sms, stream);
   return dtype == DT_BF16 ? launch_one<DT_BF16, false, false, 3>(p, num_sms, stream) : launch_one<DT_FP16, false, false, 3>(p, num_sms, stream);
