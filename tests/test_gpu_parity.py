@@ -325,6 +325,49 @@ def test_pair_dw_kernel_matches_oracle(hidden, skip, mode):
     assert worst < TOL_GRAD_REL[mode]
 
 
+_PAIR_SCRIPT = r"""
+import json, sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/oracle")
+import sdf_oracle as orc
+import sdf_representation_b200 as pkg
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+net = pkg.ImplicitNet(3, [512] * 8, (4,), 100.0, True, precision="fast").to(dev)
+g = torch.Generator().manual_seed(5)
+x = torch.rand(1500, 3, generator=g) * 2 - 1
+y = orc.torus_labels(x).float()
+f = net(x.to(dev))
+loss = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)(x.to(dev), y.to(dev), net, 0)
+loss.backward()
+print(json.dumps({"f": f[:, 0].cpu().tolist(), "loss": float(loss),
+                  "grads": [p.grad.flatten()[:4096].cpu().tolist() for p in net.parameters()]}))
+"""
+
+
+def test_chain_cta_pair_and_single_cta_agree():
+    """The layer chain runs on single CTAs or on CTA pairs (cta_group::2, second weight layout; default: pairs for the
+    training programs).  Forcing either everywhere (SDFNET_PAIR=0 / 1) must give the same forward values, loss and
+    parameter gradients up to the accumulation order of the tensor cores."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, SDFNET_PAIR=mode)
+        out = subprocess.run([sys.executable, "-c", _PAIR_SCRIPT, root], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[mode] = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    a, b = res["0"], res["1"]
+    df = np.abs(np.array(a["f"]) - np.array(b["f"])).max()
+    worst = max(rel_err(torch.tensor(ga), torch.tensor(gb)) for ga, gb in zip(a["grads"], b["grads"]))
+    print(f"pair vs single CTA: max|df| {df:.3e}  loss {a['loss']:.7f} / {b['loss']:.7f}  worst grad rel {worst:.3e}")
+    assert df < 1e-4
+    assert abs(a["loss"] - b["loss"]) < 1e-5
+    assert worst < 2e-3
+
+
 def test_bf16_operand_mode_runs_and_is_bounded():
     """dtype="bf16" (8-bit mantissa operands, same kernels with the bf16 MMA kind and bf16 packed epilogue math): f, grad
     and the IGRLOSS gradients stay within the looser bf16 bound stated in DESIGN.md (errors ~8x the fp16 fast mode)."""
