@@ -64,6 +64,15 @@ namespace sdf {
 #ifndef SDF_L2PF_REV
 #define SDF_L2PF_REV 0  // (A/B: 3-5 % slower for the reverse sweep, twice)
 #endif
+// relay loops of the peer CTA (CTA-pair kernel): poll with test_wait (no suspend) instead of try_wait
+#ifndef SDF_RELAY_SPIN
+#define SDF_RELAY_SPIN 0
+#endif
+#if SDF_RELAY_SPIN
+#define RELAY_WAIT mbar_wait_spin
+#else
+#define RELAY_WAIT mbar_wait
+#endif
 #ifndef SDF_PACKED_ALL
 #define SDF_PACKED_ALL 0
 #endif
@@ -1091,7 +1100,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           for (int s = 0; s < p.n_steps; ++s) {
             const int nchunks = p.steps[s].n_groups * p.steps[s].kchunks;
             for (int c = 0; c < nchunks; ++c) {
-              mbar_wait(&w_full[stage], round & 1);
+              RELAY_WAIT(&w_full[stage], round & 1);
               mbar_arrive_cluster(&peer_full[stage], 0);
               if (++stage == NST) { stage = 0; ++round; }
             }
@@ -1232,7 +1241,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           for (int s = 0; s < p.n_steps; ++s) {
             if (p.steps[s].n_groups == 0) continue;
             for (int j = 0; j < 4; ++j) {
-              mbar_wait(&B.a_q[j], n0 & 1);
+              RELAY_WAIT(&B.a_q[j], n0 & 1);
               tc_fence_after();
               tc_fence_before();
               mbar_arrive_cluster(&a_qr[j], 0);

@@ -44,6 +44,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking poll (mbarrier.test_wait has no hardware suspend: lowest wake-up latency, for single-thread relay loops)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > SDF_SPIN_LIMIT * 16u) __trap();
+  }
+}
 // Returns when the phase with the given parity has completed.  Traps after SDF_SPIN_LIMIT polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -302,7 +317,13 @@ __device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t cta_mask) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+#ifdef SDF_REMOTE_ARRIVE_RELEASE_CLUSTER
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#else
+  // default semantics (.release.cta), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses for its 2-SM hand-shakes:
+  // the .release.cluster form costs a MEMBAR.ALL + ERRBAR per arrival (ncu), which is pure latency in a relay warp
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#endif
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
