@@ -345,9 +345,9 @@ print(json.dumps({"f": f[:, 0].cpu().tolist(), "loss": float(loss),
 
 
 def test_chain_cta_pair_and_single_cta_agree():
-    """The layer chain runs on single CTAs or on CTA pairs (cta_group::2, second weight layout; default: pairs for the
-    training programs).  Forcing either everywhere (SDFNET_PAIR=0 / 1) must give the same forward values, loss and
-    parameter gradients up to the accumulation order of the tensor cores."""
+    """The layer chain runs on CTA pairs (cta_group::2, second weight layout; the default at width 512 in fast mode) or on
+    single CTAs (SDFNET_PAIR=0).  Both must give the same forward values, loss and parameter gradients up to the
+    accumulation order of the tensor cores."""
     import json
     import subprocess
     import sys
