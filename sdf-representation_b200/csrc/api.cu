@@ -16,7 +16,8 @@ cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* d
                                 int k16, int kind, float scale, int dtype, int split, int halves, cudaStream_t stream);
 cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream);
 cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
-cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
+cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, int* sync_ctr, int group,
+                       cudaStream_t stream);
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
                              float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
                              int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
@@ -115,6 +116,9 @@ struct sdfnet_handle {
   double* fbar_sum = nullptr;
   GradLayout gl;
   DwItem* items_dev = nullptr;
+  int* dw_sync = nullptr;          // lock-step counters of the CTA-pair weight-gradient kernel, one per group of items
+  int dw_sync_cap = 0;
+  int dw_group = 1;                // items per group (the blocks of one layer and tile range that share operand tiles)
   int items_cap = 0;
   int items_n = 0;                 // cached work list: valid for (items_ws, items_tiles, items_so)
   int items_pair_n = 0;            // the first items_pair_n entries are 256 x 256 blocks for the CTA-pair kernel
@@ -269,6 +273,7 @@ extern "C" int sdfnet_destroy(sdfnet_t h) {
   cudaFree(h->scale_dev);
   cudaFree(h->absmax_dev);
   cudaFree(h->items_dev);
+  cudaFree(h->dw_sync);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   delete h;
@@ -567,7 +572,7 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   auto launch_both = [&]() -> int {
     Launch lr(h, PC_DW, stream, h->items_pair_n > 0 && h->items_n > h->items_pair_n ? 2 : 1);
     if (h->items_pair_n > 0)
-      CU(launch_dw2(h->items_dev, h->items_pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+      CU(launch_dw2(h->items_dev, h->items_pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, h->dw_sync, h->dw_group, stream));
     if (h->items_n > h->items_pair_n)
       CU(launch_dw(h->items_dev + h->items_pair_n, h->items_n - h->items_pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
     return 0;
@@ -588,6 +593,19 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
     const int nb2 = H / 256;
     const int types = (L - 1) * nb2 * nb2;
     int ksplit = (8 * (h->num_sms / 2) + types - 1) / types;
+    h->dw_group = getenv("SDFNET_DW_NOSYNC") ? 1 : nb2 * nb2;
+    if (h->dw_group > 1) {
+      // lock-step groups (dw.cu): deal the items over a multiple-of-group number of pairs with no ragged last round
+      const int pairs_eff = (h->num_sms / 2) / h->dw_group * h->dw_group;
+      if (pairs_eff > 0) {
+        int a = types, b = pairs_eff;
+        while (b) { const int t = a % b; a = b; b = t; }
+        const int step = pairs_eff / a;  // ksplit must be a multiple of this for (ksplit * types) % pairs_eff == 0
+        int k2 = (ksplit + step / 2) / step * step;
+        if (k2 < step) k2 = step;
+        if (k2 <= tiles) ksplit = k2;
+      }
+    }
     if (ksplit > tiles) ksplit = tiles;
     if (ksplit < 1) ksplit = 1;
     for (int sp = 0; sp < ksplit; ++sp) {
@@ -675,6 +693,15 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
     h->items_cap = 0;
     CU(cudaMalloc(&h->items_dev, sizeof(DwItem) * n_items));
     h->items_cap = n_items;
+  }
+  if (pair_n / (h->dw_group > 0 ? h->dw_group : 1) + 1 > h->dw_sync_cap) {
+    CU(cudaStreamSynchronize(stream));
+    cudaFree(h->dw_sync);
+    h->dw_sync = nullptr;
+    h->dw_sync_cap = 0;
+    const int need = pair_n + 64;
+    CU(cudaMalloc(&h->dw_sync, sizeof(int) * need));
+    h->dw_sync_cap = need;
   }
   // the list is rebuilt per call from a pageable host vector: a synchronous copy keeps it simple and safe
   CU(cudaMemcpyAsync(h->items_dev, items.data(), sizeof(DwItem) * n_items, cudaMemcpyHostToDevice, stream));

@@ -172,10 +172,14 @@ constexpr uint32_t kDw2Half = 16 * kGranuleBytes;        // 128 features x 128 p
 constexpr uint32_t kDw2XBytes = kGranuleBytes;            // this CTA's 8 columns of a 16-column block image
 constexpr uint32_t kDw2StageBytes = 2 * kDw2Half + kDw2XBytes;  // A half + B half + block-image granule
 constexpr uint32_t kDw2Smem = kDw2Stages * kDw2StageBytes + 256;
+#ifndef SDF_DW_SYNC_TILES
+#define SDF_DW_SYNC_TILES 4
+#endif
+constexpr int kDw2SyncTiles = SDF_DW_SYNC_TILES;  // tiles between two lock-step points of a group of pairs (power of two)
 
 template <int DT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1)
-dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
+dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity, int* __restrict__ sync_ctr, int group, int n_pairs_eff) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDw2Stages * kDw2StageBytes);
   uint64_t* full = bars;                         // [3] local: this CTA's halves have landed
@@ -186,7 +190,11 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // Work items are dealt to the first n_pairs_eff pairs only (a multiple of the group size): the `group` consecutive
+  // items that share operand tiles (the four 256 x 256 blocks of one layer and tile range) are then always processed by
+  // `group` neighbouring pairs in the same round, and those pairs keep in step (sync_ctr, see the producer) so that the
+  // second read of every half tile is an L2 hit instead of a DRAM read.
+  const int pair = (static_cast<int>(blockIdx.x >> 1) < n_pairs_eff) ? static_cast<int>(blockIdx.x >> 1) : n_items, n_pairs = n_pairs_eff;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kDw2Stages; ++i) {
@@ -217,6 +225,17 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
             const uint8_t* a = (term ? d.A2 : d.A1) + static_cast<size_t>(tile) * d.a_tstride + d.a_off + rank * kDw2Half;
             const uint8_t* b = (term ? d.B2 : d.B1) + static_cast<size_t>(tile) * d.b_tstride + d.b_off + rank * kDw2Half;
             const bool with_x = d.X != nullptr && term == 0;
+            if (group > 1 && rank == 0 && term == 0 && ((tile - d.tile0) & (kDw2SyncTiles - 1)) == 0) {
+              // lock-step with the other pairs of the group every kDw2SyncTiles tiles: one arrival per pair, then wait
+              // until all `group` pairs have arrived at this point of this item
+              int* ctr = sync_ctr + it / group;
+              const int target = group * (static_cast<int>(tile - d.tile0) / kDw2SyncTiles + 1);
+              atomicAdd(ctr, 1);
+              uint32_t spins = 0;
+              while (*reinterpret_cast<volatile int*>(ctr) < target) {
+                if (++spins > SDF_SPIN_LIMIT) { printf("sdf: dw2 group sync timeout (pair %d item %d)\n", pair, it); __trap(); }
+              }
+            }
             mbar_wait(&empty[stage], (round & 1) ^ 1);
             mbar_arrive_expect_tx(&full[stage], 2 * kDw2Half + (with_x ? kDw2XBytes : 0u));
             uint8_t* dst = smem + stage * kDw2StageBytes;
@@ -365,7 +384,8 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity) {
   if (warp == 5) tmem_dealloc2<512>(tmem_base);
 }
 
-cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream) {
+cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, int* sync_ctr, int group,
+                       cudaStream_t stream) {
   static bool attr_set[2] = {false, false};
   auto kfn = dtype == DT_BF16 ? dw2_kernel<DT_BF16> : dw2_kernel<DT_FP16>;
   if (!attr_set[dtype]) {
@@ -376,7 +396,20 @@ cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int pari
   if (n_items <= 0) return cudaSuccess;
   int pairs = num_sms / 2;
   if (n_items < pairs) pairs = n_items;
-  kfn<<<2 * pairs, kDwThreads, kDw2Smem, stream>>>(items_dev, n_items, parity);
+  // lock-step groups need every group inside one round of the item deal: pairs_eff is a multiple of the group size and
+  // all of them are co-resident (one CTA per SM), so the group barrier cannot deadlock
+  int pairs_eff = pairs;
+  if (group > 1 && sync_ctr) {
+    pairs_eff = pairs / group * group;
+    if (pairs_eff == 0 || n_items % group != 0) { pairs_eff = pairs; group = 1; }
+  } else {
+    group = 1;
+  }
+  if (group > 1) {
+    cudaError_t e = cudaMemsetAsync(sync_ctr, 0, sizeof(int) * (n_items / group), stream);
+    if (e != cudaSuccess) return e;
+  }
+  kfn<<<2 * pairs, kDwThreads, kDw2Smem, stream>>>(items_dev, n_items, parity, sync_ctr, group, pairs_eff);
   return cudaGetLastError();
 }
 
