@@ -173,7 +173,7 @@ constexpr uint32_t kDw2XBytes = kGranuleBytes;            // this CTA's 8 column
 constexpr uint32_t kDw2StageBytes = 2 * kDw2Half + kDw2XBytes;  // A half + B half + block-image granule
 constexpr uint32_t kDw2Smem = kDw2Stages * kDw2StageBytes + 256;
 #ifndef SDF_DW_SYNC_TILES
-#define SDF_DW_SYNC_TILES 4
+#define SDF_DW_SYNC_TILES 8
 #endif
 constexpr int kDw2SyncTiles = SDF_DW_SYNC_TILES;  // tiles between two lock-step points of a group of pairs (power of two)
 
