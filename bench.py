@@ -31,8 +31,8 @@ TRAIN_FLOP = 6 * F_FLOP       # algorithmic FLOP per IGRLOSS training point (fwd
 POINTS_PER_GPU = 1 << 20
 N_BATCHES = 8                 # distinct resident batches cycled through: 8 x 28 MB = 224 MB > 126 MB L2
 # measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this command at
-# 1M points, profiles/r01p_train_step_1M_ncu.txt) per point and kernel class; roofline.traffic scales it to the launch
-NCU_DRAM_BYTES_PER_POINT = {"chain_fwd_rev": 22668.0, "chain_tan_adj": 61913.0, "dw_gemm": 46221.0}
+# 1M points, profiles/r01q_train_step_1M_ncu.txt) per point and kernel class; roofline.traffic scales it to the launch
+NCU_DRAM_BYTES_PER_POINT = {"chain_fwd_rev": 22665.0, "chain_tan_adj": 62263.0, "dw_gemm": 28829.0}
 METRIC = "train_points_per_s"
 UNIT = "points/s"
 
@@ -309,7 +309,7 @@ def main():
         "roofline": {
             "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved / peak_tf, "traffic": NCU_DRAM_BYTES_PER_POINT[dom] * pts_per_launch,
-            "traffic_source": "ncu --set full, profiles/r01p_train_step_1M_ncu.txt (bytes/point of this kernel x points per launch)",
+            "traffic_source": "ncu --set full, profiles/r01q_train_step_1M_ncu.txt (bytes/point of this kernel x points per launch)",
             "peak_source": peak_src,
             "per_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
             "algorithmic_flop_per_point_this_kernel": 2 * F_FLOP,
