@@ -24,10 +24,16 @@
 // Warp roles (640 threads = 5 warpgroups; setmaxnreg moves registers from the last warpgroup to the epilogue):
 //   warps 0-15  epilogue: warp w owns TMEM lanes 32*(w%4).. (tile rows) and column quarter w/4 of every 128-column block
 //   warp 16     weight producer (cp.async.bulk into a 3-stage ring)
-//   warp 17     MMA issuer (one elected thread)
-//   warps 18-19 idle
+//   warp 17     MMA issuer: warp-uniform loop, one elected lane issues (pair kernel, peer CTA: "my weight half has
+//               landed" relay)
+//   warp 18     pair kernel, peer CTA: relays the completed A-image quarters to the leader CTA; otherwise idle
+//   warp 19     idle
 // Four epilogue warps per SM sub-partition give the latency hiding (TMEM reads, spill-image loads, MUFU) that the
-// accumulator hand-off needs; the arithmetic itself is MUFU-bound in the forward sweep (ex2 + lg2 per element).
+// accumulator hand-off needs.
+//
+// At width 512 in fast mode the kernel runs on CTA pairs by default (PAIR = true: cluster of 2, tcgen05 cta_group::2,
+// each CTA streams half of every weight chunk); the single-CTA form serves the other widths, the parity mode and
+// SDFNET_PAIR=0.  Each form is instantiated per program family (SW: forward / reverse, tangent / adjoint).
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cstdio>

@@ -325,6 +325,36 @@ def test_pair_dw_kernel_matches_oracle(hidden, skip, mode):
     assert worst < TOL_GRAD_REL[mode]
 
 
+@pytest.mark.parametrize("n", [1, 129, 300, 641])
+def test_cta_pair_ragged_tile_counts(n):
+    """Width 512 in fast mode runs the chain on CTA pairs that walk tiles two at a time: odd tile counts (the peer of
+    the last pair works on a scratch tile), a single point, and ragged tails -- f, grad_x f and an IGRLOSS step against the
+    fp64 oracle."""
+    import sdf_representation_b200 as pkg
+
+    torch.manual_seed(21)
+    L = 3
+    net = pkg.ImplicitNet(3, [512] * L, (2,), 100.0, True, precision="fast").to(dev())
+    g = torch.Generator().manual_seed(22 + n)
+    x = torch.rand(n, 3, generator=g) * 2 - 1
+    y = orc.torus_labels(x)
+    W = [getattr(net, f"lin{i}").weight.detach().double().cpu() for i in range(L + 1)]
+    b = [getattr(net, f"lin{i}").bias.detach().double().cpu() for i in range(L + 1)]
+    f_ref, g_ref = orc.forward_and_gradient(W, b, x.double(), (2,), 100.0)
+    f, gr = net.sdf_and_gradient(x.to(dev()))
+    assert float((f[:, 0].cpu().double() - f_ref).abs().max()) < TOL_FAST_F
+    assert float((gr.cpu().double() - g_ref).abs().max()) < TOL_FAST_G
+    f_only = net(x.to(dev()))
+    assert float((f_only[:, 0].cpu().double() - f_ref).abs().max()) < TOL_FAST_F
+    loss_ref, _, dW, db = orc.igr_loss_and_grads(W, b, x.double(), y.double(), (2,), 100.0)
+    loss = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)(x.to(dev()), y.float().to(dev()), net, 0)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < 5e-3 * max(1.0, abs(float(loss_ref)))
+    if n > 1:
+        worst = max(rel_err(getattr(net, f"lin{i}").weight.grad.cpu(), dW[i].float()) for i in range(L + 1))
+        assert worst < TOL_GRAD_REL["fast"], worst
+
+
 _PAIR_SCRIPT = r"""
 import json, sys, torch
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/oracle")
