@@ -409,6 +409,30 @@ cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int pari
     cudaError_t e = cudaMemsetAsync(sync_ctr, 0, sizeof(int) * (n_items / group), stream);
     if (e != cudaSuccess) return e;
   }
+  if (group > 1) {
+    // The group barrier needs every CTA of the grid resident at once.  On an idle GPU that is what happens anyway (one
+    // CTA per SM by shared memory); a cooperative launch makes it a guarantee when another stream's kernel holds SMs
+    // (gang scheduling) instead of a possible deadlock.  If the launch is refused, run without the lock-step.
+    static bool coop_ok = true;
+    if (coop_ok) {
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.gridDim = dim3(2 * pairs);
+      cfg.blockDim = dim3(kDwThreads);
+      cfg.dynamicSmemBytes = kDw2Smem;
+      cfg.stream = stream;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, items_dev, n_items, parity, sync_ctr, group, pairs_eff);
+      if (e == cudaSuccess) return cudaGetLastError();
+      cudaGetLastError();  // clear; fall back below
+      coop_ok = false;
+    }
+    group = 1;
+    pairs_eff = pairs;
+  }
   kfn<<<2 * pairs, kDwThreads, kDw2Smem, stream>>>(items_dev, n_items, parity, sync_ctr, group, pairs_eff);
   return cudaGetLastError();
 }
