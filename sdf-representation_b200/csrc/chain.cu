@@ -62,34 +62,10 @@ namespace sdf {
 #define SDF_REGS_EPI 104
 #define SDF_REGS_AUX 56
 #endif
-#ifndef SDF_COPY_SPLIT
-#define SDF_COPY_SPLIT 1
-#endif
-// reverse sweep: request the step's activation-image lines into L2 at the start of the step (ncu: almost all of them
-// come from DRAM - 6.7 GB read per 1M points - although the forward sweep of the same tile wrote them moments earlier)
-#ifndef SDF_L2PF_REV
-#define SDF_L2PF_REV 0  // (A/B: 3-5 % slower for the reverse sweep, twice)
-#endif
-// relay loops of the peer CTA (CTA-pair kernel): poll with test_wait (no suspend) instead of try_wait
-#ifndef SDF_RELAY_SPIN
-#define SDF_RELAY_SPIN 0
-#endif
-#if SDF_RELAY_SPIN
-#define RELAY_WAIT mbar_wait_spin
-#else
-#define RELAY_WAIT mbar_wait
-#endif
-#ifndef SDF_PACKED_ALL
-#define SDF_PACKED_ALL 0
-#endif
-#ifndef SDF_PF_NEXT
-#define SDF_PF_NEXT 0  // (requesting the next step's images one step ahead measured 18 % slower: L2 thrash)
-#endif
 #ifndef SDF_ISSUER_UNROLL
 #define SDF_ISSUER_UNROLL 1
 #endif
 
-constexpr int kCopySplit = SDF_COPY_SPLIT;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kProducerWarp = kEpiWarps;
@@ -145,30 +121,6 @@ __device__ __forceinline__ uint4 ld_smem_v4(uint32_t addr) {
   return v;
 }
 
-// L2 eviction-priority hints for the u image: written by the tangent sweep and read back by the adjoint sweep of the same
-// tile (evict_last while it waits, evict_first on its only read), so that part of its 2 KB / point / layer round trip
-// stays in L2 now that the tangent + adjoint kernel runs at ~80 % of the HBM copy bandwidth.
-#ifndef SDF_U_POLICY
-#define SDF_U_POLICY 0
-#endif
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void st_global_policy(uint8_t* ptr, const uint4& v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint4 ld_global_policy(const uint8_t* ptr, uint64_t pol) {
-  uint4 v;
-  asm volatile("ld.global.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol));
-  return v;
-}
 template <int DT>
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 o;
@@ -331,9 +283,6 @@ struct StepIO {
   uint8_t* out;         // spill image of the result (nullptr: not spilled)
   uint8_t* out_u;       // tangent: u image
   const float* vec;     // forward: bias row
-  const uint8_t* pf_a;  // tangent / adjoint: the next step's in_a / in_b images (requested into L2 one step ahead)
-  const uint8_t* pf_b;
-  bool pf_now;          // also request this step's images (first step of a sweep)
   bool special;         // the last three columns of this layer carry the raw input (skip injection)
 };
 
@@ -436,15 +385,7 @@ __device__ __forceinline__ void load_aux(const Epi& e, const StepIO& io, int c, 
     }
   } else {
     ldg_piece<PAR>(e, c, io.in_a, xa);
-    if (io.in_b) {
-      if (SDF_U_POLICY && !PAR && EPI == EPI_ADJ_HIDDEN) {
-        const uint64_t pol = l2_policy_evict_first();  // the adjoint sweep is the only reader of u
-#pragma unroll
-        for (int j = 0; j < 2; ++j) xb.h[j] = ld_global_policy(io.in_b + img_off(c + 8 * j, e.prow), pol);
-      } else {
-        ldg_piece<PAR>(e, c, io.in_b, xb);
-      }
-    }
+    if (io.in_b) ldg_piece<PAR>(e, c, io.in_b, xb);
   }
 }
 
@@ -622,26 +563,6 @@ __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& 
     }
   } else {
     uint32_t uo[4];
-#if SDF_PACKED_ALL
-    // everything on packed pairs: the accumulator pair is rounded to 16 bits first (the result is stored in 16 bits
-    // anyway), then one packed multiply-add per term
-    const uint32_t one2 = H16<DT>::pack(1.f, 1.f), beta2 = H16<DT>::pack(k.beta, k.beta);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t e2 = P2<DT>::ex2(P2<DT>::mul(word(xa, i), nbl2_2));  // exp(-beta a) = 1 - act'(z)
-      const uint32_t vh = H16<DT>::pack(v[2 * i], v[2 * i + 1]);
-      if (EPI == EPI_REV_HIDDEN) {
-        o[i] = P2<DT>::mul(vh, P2<DT>::sub(one2, e2));
-      } else if (EPI == EPI_TAN_HIDDEN) {
-        const uint32_t wh = P2<DT>::mul(vh, e2);                 // (1 - s') zdot
-        o[i] = P2<DT>::sub(vh, wh);                              // adot = s' zdot
-        uo[i] = P2<DT>::mul(P2<DT>::mul(wh, beta2), word(xb, i));  // u = beta (1 - s') zdot q
-      } else {  // EPI_ADJ_HIDDEN
-        const uint32_t sp = P2<DT>::sub(one2, e2);
-        o[i] = has_b ? P2<DT>::fma(vh, sp, word(xb, i)) : P2<DT>::mul(vh, sp);  // s' r + u
-      }
-    }
-#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 ef = H16<DT>::unpack(P2<DT>::ex2(P2<DT>::mul(word(xa, i), nbl2_2)));  // exp(-beta a) = 1 - act'(z)
@@ -657,7 +578,6 @@ __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& 
         if (has_b) o[i] = P2<DT>::add(o[i], word(xb, i));       // + u
       }
     }
-#endif
     if (EPI == EPI_TAN_HIDDEN) *ou = make_uint4(uo[0], uo[1], uo[2], uo[3]);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
@@ -698,16 +618,6 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
   }
 }
 
-// Spill-image store.  Images that are next read by a later kernel (q, adot, Zbar) are written with the streaming
-// (evict-first) policy so they do not push the lines this kernel still needs (prefetched operands, weights) out of L2.
-#ifndef SDF_STCS
-#define SDF_STCS 0  // (A/B on B200: no measurable difference)
-#endif
-template <int EPI>
-__device__ __forceinline__ void store_spill(uint8_t* ptr, const uint4& v) {
-  if (SDF_STCS && EPI != EPI_FWD_HIDDEN) __stcs(reinterpret_cast<uint4*>(ptr), v);
-  else *reinterpret_cast<uint4*>(ptr) = v;
-}
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // Hidden-layer epilogue, overlapped form (fast mode, H = 512: two accumulator halves of 256 columns).
@@ -725,25 +635,15 @@ template <int DT, int EPI>
 __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
 #ifndef SDF_NO_L2PF
-  // Every spill-image line a step reads is first requested into L2: this step's lines by the first step of a sweep,
-  // the next step's lines by every step (one step = ~15 us ahead of their use).
+  // Every spill-image line the step will read is first requested into L2 (same-session A/B on B200: +3 % for the
+  // tangent / adjoint sweeps, whose operands come from HBM; requesting the *next* step's lines instead: -18 %, L2 thrash)
   if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) {
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t o = img_off(ci * 128 + e.h * 32 + 8 * j, e.prow);
-        if (SDF_PF_NEXT) {
-          if (io.pf_now) {
-            prefetch_l2(io.in_a + o);
-            if (io.in_b) prefetch_l2(io.in_b + o);
-          }
-          if (io.pf_a) prefetch_l2(io.pf_a + o);
-          if (io.pf_b) prefetch_l2(io.pf_b + o);
-        } else {
-          prefetch_l2(io.in_a + o);
-          if (io.in_b) prefetch_l2(io.in_b + o);
-        }
+        prefetch_l2(io.in_a + img_off(ci * 128 + e.h * 32 + 8 * j, e.prow));
+        if (io.in_b) prefetch_l2(io.in_b + img_off(ci * 128 + e.h * 32 + 8 * j, e.prow));
       }
     }
   }
@@ -822,17 +722,14 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
         } else {
           uint4 ou;
           pq[j] = granule_fast<DT, EPI>(w, xa.h[j], xb.h[j], k, nbl2_2, io.in_b != nullptr, &ou);
-          if (EPI == EPI_TAN_HIDDEN) {
-            if (SDF_U_POLICY) st_global_policy(io.out_u + img_off(c + 8 * j, e.prow), ou, l2_policy_evict_last());
-            else *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
-          }
+          if (EPI == EPI_TAN_HIDDEN) *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
         }
       }
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
       const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       if (io.out) {
-        store_spill<EPI>(io.out + img_off(c, e.prow), p0);
-        store_spill<EPI>(io.out + img_off(c + 8, e.prow), p1);
+        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = p0;
+        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = p1;
       }
       if (half == 0) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
@@ -866,10 +763,6 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
 #ifndef SDF_AUX_AHEAD
 #define SDF_AUX_AHEAD 14
 #endif
-// sweeps (same bit mask) whose spill-image operands are requested two pieces ahead instead of one (unrolled halves only)
-#ifndef SDF_AUX_DIST2
-#define SDF_AUX_DIST2 0
-#endif
 template <int DT, int EPI>
 __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
@@ -882,11 +775,11 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
   constexpr bool kTmemAhead = (SDF_TMEM_AHEAD & kSweepBit) != 0;
   constexpr bool kAuxAhead = !kFwd && (SDF_AUX_AHEAD & kSweepBit) != 0;
   constexpr int kUnrollHalves = (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) ? 1 : 2;
-  constexpr int kAuxDist = !kAuxAhead ? 0 : ((SDF_AUX_DIST2 & kSweepBit) != 0 && kUnrollHalves == 2) ? 2 : 1;
+  constexpr int kAuxDist = kAuxAhead ? 1 : 0;  // (two pieces ahead in the reverse sweep: no gain measured)
 #ifndef SDF_NO_L2PF
   // (same-session A/B on B200: +3 % for the tangent / adjoint sweeps, whose operands come from HBM; -2 % for the
   // reverse sweep, whose activation images were written moments earlier and are mostly still in L2)
-  if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN || (EPI == EPI_REV_HIDDEN && SDF_L2PF_REV)) {
+  if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) {
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
@@ -899,10 +792,9 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #endif
   const uint32_t nbl2_2 = H16<DT>::pack(k.nbl2, k.nbl2);
   const int cb = e.h * 32;  // this thread's column offset inside every 128-column block
-  Piece<false> xa[3], xb[3];
+  Piece<false> xa[2], xb[2];
   uint32_t r[2][16];
   load_aux<false, EPI>(e, io, cb, xa[0], xb[0]);
-  if (kAuxDist == 2) load_aux<false, EPI>(e, io, cb + 16, xa[1], xb[1]);
   CLK_DECL;
   mbar_wait(&B.acc_full[0], par0);
   tc_fence_after();
@@ -941,9 +833,8 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #pragma unroll
     for (int pc = 0; pc < 4; ++pc) {
       // piece pc of this half: chunk pc / 2, 16-column sub-piece pc % 2
-      const int P = half * 4 + pc;  // piece index of the step (compile-time when the halves are unrolled)
       const int cur = pc & 1, nxt = cur ^ 1;
-      const int ac = kAuxDist == 2 ? P % 3 : cur;  // buffer holding this piece's spill-image operands
+      const int ac = cur;  // buffer holding this piece's spill-image operands
       const int c0 = half * 256 + (pc >> 1) * 128 + cb;  // chunk base column
       const int c = c0 + (pc & 1) * 16;                  // first column of the piece
       const int cn = pc < 3 ? half * 256 + ((pc + 1) >> 1) * 128 + cb + ((pc + 1) & 1) * 16 : 256 + cb;  // next piece
@@ -952,10 +843,6 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       tmem_ld_wait();
       if (kTmemAhead && pc < 3) tmem_ld16(e.taddr + cn, r[nxt]);
       if (kAuxDist == 1 && (pc < 3 || half == 0)) load_aux<false, EPI>(e, io, cn, xa[nxt], xb[nxt]);
-      if (kAuxDist == 2 && P + 2 < 8) {
-        const int P2 = P + 2;
-        load_aux<false, EPI>(e, io, (P2 >> 2) * 256 + ((P2 & 3) >> 1) * 128 + cb + (P2 & 1) * 16, xa[P2 % 3], xb[P2 % 3]);
-      }
       uint4 pq[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -964,15 +851,12 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
         for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r[cur][8 * j + t]);
         uint4 ou;
         pq[j] = granule_fast<DT, EPI>(w, xa[ac].h[j], xb[ac].h[j], k, nbl2_2, io.in_b != nullptr, &ou);
-        if (EPI == EPI_TAN_HIDDEN) {
-          if (SDF_U_POLICY) st_global_policy(io.out_u + img_off(c + 8 * j, e.prow), ou, l2_policy_evict_last());
-          else *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
-        }
+        if (EPI == EPI_TAN_HIDDEN) *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
       }
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
       if (io.out) {
-        store_spill<EPI>(io.out + img_off(c, e.prow), pq[0]);
-        store_spill<EPI>(io.out + img_off(c + 8, e.prow), pq[1]);
+        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = pq[0];
+        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = pq[1];
       }
       if (half == 0) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
@@ -1119,15 +1003,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               if (elect_one()) {
                 const uint32_t bytes = PAIR ? st.chunk_bytes / 2 : st.chunk_bytes;
                 mbar_arrive_expect_tx(&w_full[stage], bytes);
-                // one stage = kCopySplit concurrent bulk copies (a single copy does not saturate the L2 -> SM path)
-                const uint32_t part = bytes / kCopySplit;
-                const uint8_t* gsrc = src + static_cast<size_t>(c) * st.chunk_bytes + rank * bytes;
-                if ((part & 15u) == 0) {
-#pragma unroll
-                  for (int i = 0; i < kCopySplit; ++i) bulk_g2s(sW + stage * kStage + i * part, gsrc + i * part, part, &w_full[stage]);
-                } else {
-                  bulk_g2s(sW + stage * kStage, gsrc, bytes, &w_full[stage]);
-                }
+                bulk_g2s(sW + stage * kStage, src + static_cast<size_t>(c) * st.chunk_bytes + rank * bytes, bytes, &w_full[stage]);
               }
               __syncwarp();
               if (++stage == NST) { stage = 0; ++round; }
@@ -1144,7 +1020,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           for (int s = 0; s < p.n_steps; ++s) {
             const int nchunks = p.steps[s].n_groups * p.steps[s].kchunks;
             for (int c = 0; c < nchunks; ++c) {
-              RELAY_WAIT(&w_full[stage], round & 1);
+              mbar_wait(&w_full[stage], round & 1);
               mbar_arrive_cluster(&peer_full[stage], 0);
               if (++stage == NST) { stage = 0; ++round; }
             }
@@ -1285,7 +1161,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           for (int s = 0; s < p.n_steps; ++s) {
             if (p.steps[s].n_groups == 0) continue;
             for (int j = 0; j < 4; ++j) {
-              RELAY_WAIT(&B.a_q[j], n0 & 1);
+              mbar_wait(&B.a_q[j], n0 & 1);
               tc_fence_after();
               tc_fence_before();
               mbar_arrive_cluster(&a_qr[j], 0);
@@ -1531,8 +1407,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         io.in_a = io.in_b = nullptr;
         io.out = io.out_u = nullptr;
         io.vec = nullptr;
-        io.pf_a = io.pf_b = nullptr;
-        io.pf_now = false;
         io.special = false;
         switch (st.epi) {
           case EPI_FWD_HIDDEN: if (SW & 1) {
@@ -1619,11 +1493,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             io.out = no_stg ? nullptr : img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
             io.out_u = relu ? nullptr : img_ptr(p.Uimg, l, p.tile_stride, tile, ib);
             io.special = l == inj_layer;
-            io.pf_now = l == 0;
-            if (l + 1 < p.L) {
-              io.pf_a = img_ptr(p.Aimg, l + 1, p.tile_stride, tile, ib);
-              io.pf_b = relu ? nullptr : img_ptr(p.Qimg, l + 1, p.tile_stride, tile, ib);
-            }
             hidden_step<DT, PAR, EPI_TAN_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           case EPI_ADJ_START: if (SW & 2) {
@@ -1670,11 +1539,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             io.in_b = has_u ? img_ptr(p.Uimg, l, p.tile_stride, tile, ib) : nullptr;
             io.out = no_stg ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
             io.special = l == inj_layer;
-            io.pf_now = l == p.L - 2;
-            if (l >= 1) {
-              io.pf_a = img_ptr(p.Aimg, l - 1, p.tile_stride, tile, ib);
-              io.pf_b = has_u ? img_ptr(p.Uimg, l - 1, p.tile_stride, tile, ib) : nullptr;
-            }
             hidden_step<DT, PAR, EPI_ADJ_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           default: break;
