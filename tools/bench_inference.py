@@ -27,7 +27,7 @@ out = torch.empty(n * n * n, dtype=torch.float32, device=dev)
 ms_grid, vol = timed(lambda: inference.grid_sdf(net, n, 0, n, out=out))
 inference.mc_classify(vol[: min(n, 256)])  # warm-up at the timed size (the caching allocator then holds the 267 MB blocks)
 ms_mc, (cases, active) = timed(lambda: inference.mc_classify(vol[: min(n, 256)]))
-inference.octree_build(net, 6)
+inference.octree_build(net, 10)  # warm-up at the timed depth (caching allocator, on-demand weight layout)
 ms_oct, levels = timed(lambda: inference.octree_build(net, 10))
 per_level = []
 for lv in levels:
