@@ -115,6 +115,9 @@ class Engine:
             bp[i] = b.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sdfnet_pack_weights(self.handle, wp, bp, _stream(self.device)), "sdfnet_pack_weights")
+        # the library records the parameter pointers and packs a weight layout on first use (sdfnet.h): keep the tensors
+        # (possibly contiguous temporaries) alive until the next pack
+        self._pack_keep = keep
         self.launches += 2 * n + (n - 1) + 1
         self._packed_key = key
 
