@@ -52,7 +52,10 @@ int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out);
 int sdfnet_destroy(sdfnet_t h);
 
 /* Re-pack lin{i}.weight / lin{i}.bias (fp32 device pointers, layouts [out,in] and [out], i = 0..L) into UMMA
- * operand images.  Call after every optimizer step (executor/executor.py:177). */
+ * operand images.  Call after every optimizer step (executor/executor.py:177), right before launching.
+ * There are two image layouts (single-CTA and CTA-pair kernels): the call packs the biases and the layout(s) a program
+ * of this handle has already used; a layout that is first needed by a later launch is packed then, from the parameter
+ * pointers recorded here -- so the parameter memory must stay valid and unchanged until the next call. */
 int sdfnet_pack_weights(sdfnet_t h, const float* const* weights, const float* const* biases, void* stream);
 
 /* Bytes of scratch one point tile set needs, so callers can size `ws`: mode 0 = forward_grad, 1 = training. */
