@@ -43,6 +43,8 @@ typedef struct sdfnet_igr_cfg {
   float mean_t;         /* pairwise: global mean of clamp(S, +-delta) over the whole (multi-GPU) batch */
   int64_t n_global;     /* loss normaliser: points in the whole batch across ranks */
   const float* mean_t_dev; /* optional DEVICE pointer to mean_t (overrides mean_t; avoids a host sync per step) */
+  const double* label_stats_dev; /* optional DEVICE {sum clamp(S), N} over the whole batch (sdfnet_label_stats + cross-rank
+                                  * sum): overrides mean_t, mean_t_dev and n_global -- unequal shards need no host value */
 } sdfnet_igr_cfg;
 
 const char* sdfnet_last_error(void);
@@ -77,9 +79,19 @@ int sdfnet_grid_eval(sdfnet_t h, const float* axis, int32_t n_axis, int64_t firs
 
 /* evaluations/compare_octree_dl.py:20-36 (per-node query), batched per level: SDF at the centres of the cells
  * `keys` (3 x level-bit Morton codes, x bit highest) of the octree over [-1,1]^3; refine_flags[i] = 1 iff
- * |sdf| <= band * h_level (h_level = 2 / 2^level), the single-rounding fp32 predicate of oracle/octree.py. */
+ * |sdf| <= band * h_level (h_level = 2 / 2^level), the single-rounding fp32 predicate of oracle/sdf_oracle.py:octree_flags. */
 int sdfnet_octree_level(sdfnet_t h, const uint64_t* keys, int64_t count, int32_t level, float band, float* sdf_out,
                         uint8_t* refine_flags, void* stream);
+
+/* The whole level loop of the octree build (evaluations/compare_octree_dl.py:20-36 node queries, batched per level; SURVEY.md
+ * section 8d cfg 5) WITHOUT a host round trip per level: keys / sdf / flags are arenas of `capacity` entries, level_table
+ * (DEVICE, int64 [level_hi + 2][2]) holds {count, offset} per level.  The caller fills the keys and table rows of the
+ * levels <= max(level_lo, uni_level) (uniform levels: all 8^level Morton codes, or this rank's share); for every level the
+ * forward kernel evaluates the cell centres, its last epilogue writes the refinement flags (1 below uni_level, else
+ * |sdf| <= band * h_level), and an ordered device-side compaction appends the children of the flagged cells as the next
+ * level and writes its table row.  *overflow (device) is set if the arena was too small (children beyond it are dropped). */
+int sdfnet_octree_levels(sdfnet_t h, int32_t level_lo, int32_t level_hi, int32_t uni_level, float band, uint64_t* keys,
+                         float* sdf, uint8_t* flags, int64_t capacity, int64_t* level_table, int32_t* overflow, void* stream);
 
 /* Generic backward of the network (autograd path of model/losses.py:283-296 + loss.backward()):
  * given per-point seeds fbar = dL/df [n] (may be NULL) and gbar = dL/d(grad_x f) [n,3] (may be NULL), ACCUMULATE
@@ -108,6 +120,34 @@ int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int64_t n_globa
 /* executor/executor.py:160,177 torch.optim.Adam(lr).step() fused over the flat parameter vector. */
 int sdfnet_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* The step after loss.backward() in executor/executor.py:176-177, fused: ONE kernel unpacks the gradient accumulators
+ * (after the optional cross-rank sum, see sdfnet_grad_buffer) into state_dict order, scales them by
+ * grad_scale * (*grad_scale_dev) (the d loss / d loss seed of loss.backward(); NULL = 1) and applies torch.optim.Adam's
+ * update (no amsgrad / weight decay) IN PLACE to the fp32 parameters weights[i] / biases[i] (device pointers, layouts as
+ * sdfnet_pack_weights); exp_avg / exp_avg_sq are flat [num_params] in state_dict order; grads_out (optional, flat
+ * [num_params]) receives the gradient that was applied.  ONE more kernel re-packs the operand images, bias rows and
+ * last-layer vector from the updated parameters (what sdfnet_pack_weights does), so the next step can launch at once. */
+int sdfnet_fused_adam_step(sdfnet_t h, float* const* weights, float* const* biases, float* exp_avg, float* exp_avg_sq, float lr,
+                           float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* grad_scale_dev,
+                           float* grads_out, void* stream);
+
+/* model/losses.py:115 t = clamp(y[:,0], +-delta): out2 (device, double) = {sum t, n} of this shard's labels y [n,4].  Summed
+ * over ranks it is the label_stats_dev of sdfnet_igr_cfg. */
+int sdfnet_label_stats(const float* y, int64_t n, float delta, double* out2, void* stream);
+
+/* Replaces nn.DataParallel's reduce-add of 18 gradient tensors into GPU 0 (executor/executor.py:53-56): the library's
+ * gradient accumulators followed by a 32-float tail holding the running loss sums and sum(fbar) as (hi, lo) float pairs
+ * -- ONE fp32 sum-allreduce (NCCL) over [*buf, *buf + *n_floats) carries the gradients and the loss terms of a step.
+ * The buffer stays owned by the library; it is valid between sdfnet_train_step_* / sdfnet_backward and the next
+ * sdfnet_zero_grads. */
+int sdfnet_grad_buffer(sdfnet_t h, float** buf, int64_t* n_floats);
+
+/* Loss value of the last step(s) from the tail of the gradient buffer (after the cross-rank sum): out4 (device) =
+ * {total, term0, term1, term2}; n_global <= 0: the point count that travelled with the sums.  kind 0: IGRLOSS model/losses.py:118-136 {data, normal, eikonal};
+ * kind 1: point-cloud loss executor/executordistributed.py:73-79 {surface, eikonal, 0}. */
+int sdfnet_loss_value(sdfnet_t h, int32_t kind, float tau, float lambda_g, int32_t data_term, int64_t n_global, int64_t m_global,
+                      float* out4, void* stream);
 
 /* executor/executor.py:388 marching_cubes(level=0) -- cell classification only: for the (nx-1)(ny-1)(nz-1) cells
  * of an sdf block [nx,ny,nz], case_index (8-bit corner sign mask, bit c set iff corner c < 0) and the compacted

@@ -153,11 +153,102 @@ def case_full():
     )
 
 
+def ref_igr_pointwise(model, x, y, delta, tau, lambda_g, thr):
+    """IGRLOSS with the per-point data term mean((p_i - t_i)^2) the authors presumably meant, built from the
+    reference's own pieces: model/networks.py forward, model/losses.py:283-296 compute_normal and the expressions of
+    model/losses.py:114-136 with ``predicted_sdf[:, 0]`` in place of the broadcasting ``predicted_sdf``."""
+    pred = model(x)
+    p = torch.clamp(pred, -delta, delta)[:, 0]
+    t = torch.clamp(y[:, 0], -delta, delta)
+    data = (p - t) ** 2
+    g = ref_losses.compute_normal(model, x)
+    n_true = y[:, 1:]
+    cos = torch.nn.functional.cosine_similarity(n_true, g / torch.norm(g), dim=-1)
+    reg = torch.where(torch.abs(t) < thr, (1 - cos) ** 2, torch.tensor(1e-8))
+    eik = torch.where(torch.abs(t) < thr, (g.norm(2, dim=-1) - 1) ** 2, torch.tensor(1e-8))
+    return (data + tau * reg + lambda_g * eik).mean()
+
+
+def case_round2_small():
+    """128x4 net: (1) the |t| < regularizer_threshold mask branch of model/losses.py:127-134 with thr = 0.05 < delta;
+    (2) the pointwise data term; (3) a 60-step loss curve of the reference loop body executor/executor.py:167-178
+    (zero_grad, IGRLOSS, backward, Adam.step, loss.item()) from identical seeded weights and identical batches."""
+    torch.manual_seed(7)
+    model = quiet(ref_networks.ImplicitNet, 3, [128] * 4, (2,), 100.0, True)
+    perturb(model, 11, 0.3)
+    n = 333
+    x = points(n, 1)
+    y = orc.torus_labels(x)
+    y[::17, 1:] = 0.0
+    d = {"skip": np.int64(2), "beta": np.float64(100.0), "hidden": np.int64(128), "num_hidden": np.int64(4), "x": x.numpy(), "y": y.numpy()}
+    d.update(params_np(model))
+    loss = quiet(ref_losses.IGRLOSS(0.1, 1.0, 0.1, 0.05), x.clone(), y, model, 0)
+    loss.backward()
+    d["mask_loss"] = np.float64(loss.item())
+    d["mask_frac"] = np.float64((torch.clamp(y[:, 0], -0.1, 0.1).abs() < 0.05).float().mean().item())
+    d.update(grads_np(model, "mask_grad_"))
+    for thr, tag in ((1.0, "pw"), (0.05, "pwmask")):
+        loss = ref_igr_pointwise(model, x.clone(), y, 0.1, 1.0, 0.1, thr)
+        loss.backward()
+        d[tag + "_loss"] = np.float64(loss.item())
+        d.update(grads_np(model, tag + "_grad_"))
+    # loss curve: geometric init (no perturbation), pool of 4096 points, step i trains on rows [1024 (i % 4), +1024)
+    torch.manual_seed(21)
+    model = quiet(ref_networks.ImplicitNet, 3, [128] * 4, (2,), 100.0, True)
+    pool_x = points(4096, 5)
+    pool_y = orc.torus_labels(pool_x)
+    d["curve_x"], d["curve_y"] = pool_x.numpy(), pool_y.numpy()
+    d.update({"curve_init_" + k: v for k, v in params_np(model).items()})
+    opt = torch.optim.Adam(model.parameters(), lr=4e-4)
+    crit = ref_losses.IGRLOSS(0.1, 1.0, 0.1, 1.0)
+    curve = []
+    for i in range(60):
+        lo = 1024 * (i % 4)
+        opt.zero_grad()
+        loss = quiet(crit, pool_x[lo:lo + 1024].clone(), pool_y[lo:lo + 1024], model, i)
+        loss.backward()
+        opt.step()
+        curve.append(loss.item())
+    d["curve_loss"] = np.array(curve)
+    d.update({"curve_final_" + k: v for k, v in params_np(model).items()})
+    np.savez_compressed(os.path.join(OUT, "round2_128x4.npz"), **d)
+
+
+def case_round2_full():
+    """BASELINE cfg 2 network, 8192 points (the reference's native batch scale, [N,N] data term included): per-element
+    parameter gradients of the unmodified reference, stored as a strided sample (every 61st element of each weight
+    tensor, biases in full) -- 1.84 M gradients are 7 MB."""
+    torch.manual_seed(0)
+    model = quiet(ref_networks.ImplicitNet, 3, [512] * 8, (4,), 100.0, True)
+    h = hashlib.sha256()
+    for v in model.state_dict().values():
+        h.update(v.numpy().tobytes())
+    n = 8192
+    x = points(n, 31)
+    y = orc.torus_labels(x)
+    y[::23, 1:] = 0.0
+    loss = quiet(ref_losses.IGRLOSS(0.1, 1.0, 0.1, 1.0), x.clone(), y, model, 0)
+    loss.backward()
+    d = {"weights_sha256": np.array(h.hexdigest()), "x": x.numpy(), "y": y.numpy(), "igr_loss": np.float64(loss.item()), "stride": np.int64(61)}
+    for k, p in model.named_parameters():
+        g = p.grad.detach().numpy()
+        key = "igr_grad_" + k.replace(".", "_")
+        d[key] = g.copy() if g.ndim == 1 else g.reshape(-1)[::61].copy()
+        d["igr_gnorm_" + k.replace(".", "_")] = np.float64(np.linalg.norm(g.astype(np.float64)))
+        d["igr_gmax_" + k.replace(".", "_")] = np.float64(np.abs(g).max())
+    np.savez_compressed(os.path.join(OUT, "round2_full_8x512_n8192.npz"), **d)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    case_softplus()
-    case_relu()
-    case_full()
+    which = sys.argv[1:] or ["round1", "round2"]
+    if "round1" in which:
+        case_softplus()
+        case_relu()
+        case_full()
+    if "round2" in which:
+        case_round2_small()
+        case_round2_full()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

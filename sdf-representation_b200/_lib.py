@@ -36,6 +36,7 @@ class SdfnetIgrCfg(ctypes.Structure):
         ("mean_t", c_float),
         ("n_global", c_int64),
         ("mean_t_dev", c_void_p),
+        ("label_stats_dev", c_void_p),
     ]
 
 
@@ -50,6 +51,10 @@ SIGNATURES = {
     "sdfnet_forward_grad": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sdfnet_grid_eval": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     "sdfnet_octree_level": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "sdfnet_octree_levels": (
+        c_int32,
+        [c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    ),
     "sdfnet_backward": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sdfnet_zero_grads": (c_int32, [c_void_p, c_void_p]),
     "sdfnet_read_grads": (c_int32, [c_void_p, c_void_p, c_float, c_void_p]),
@@ -66,6 +71,14 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32, c_void_p],
     ),
+    "sdfnet_fused_adam_step": (
+        c_int32,
+        [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int32,
+         c_float, c_void_p, c_void_p, c_void_p],
+    ),
+    "sdfnet_label_stats": (c_int32, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
+    "sdfnet_grad_buffer": (c_int32, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64)]),
+    "sdfnet_loss_value": (c_int32, [c_void_p, c_int32, c_float, c_float, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     "sdfnet_launch_count": (c_int64, [c_void_p]),
     "sdfnet_profile_enable": (c_int32, [c_void_p, c_int32]),
     "sdfnet_profile_read": (c_int32, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int64)]),

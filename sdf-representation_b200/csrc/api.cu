@@ -12,26 +12,32 @@
 
 namespace sdf {
 cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int pair, int num_sms, cudaStream_t stream);
-cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
-                                int k16, int kind, float scale, int dtype, int split, int halves, cudaStream_t stream);
-cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream);
 cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream);
 cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, int* sync_ctr, int group,
                        cudaStream_t stream);
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
-                             float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
-                             int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
-                             cudaStream_t stream);
+                             float lambda_g, float thr, float mean_t, const float* mean_t_dev, const double* stats_dev, double inv_n,
+                             int data_term, int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums,
+                             double* fbar_sum, cudaStream_t stream);
+cudaError_t launch_label_stats(const float* y, int64_t n, float delta, double* out2, cudaStream_t stream);
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
                              unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
                              cudaStream_t stream);
 cudaError_t launch_absmax(const float* v, int64_t n, unsigned* absmax, cudaStream_t stream);
-cudaError_t launch_seed_scale(unsigned* absmax, float* scale, cudaStream_t stream);
+cudaError_t launch_seed_scale(unsigned* absmax, float* scale, const double* sums, const double* fbar_sum, float* tail,
+                              cudaStream_t stream);
+cudaError_t launch_pack_all(const PackAll& pa, cudaStream_t stream);
+cudaError_t launch_fused_adam(int H, int L, int skip, const float* main_acc, const float* zx_acc, const float* qg_acc,
+                              const float* as_acc, const float* adx_acc, const double* fbar_sum, const float* tail, long num_params,
+                              float* const* W, float* const* b, float* m, float* v, float lr, float b1, float b2, float eps, int step,
+                              float scale, const float* scale_dev, float* grads_out, cudaStream_t stream);
+cudaError_t launch_loss_value(const float* tail, int kind, float tau, float lambda_g, int data_term, double inv_n, double inv_m,
+                              float* out4, cudaStream_t stream);
 cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream);
 cudaError_t launch_tanh_seeds(const float* f, const float* g, const float* fbar_in, const float* gbar_in, int64_t n,
                               float* fbar, float* gbar, cudaStream_t stream);
 cudaError_t launch_unpack_grads(int H, int L, int skip, const float* main_acc, const float* zx_acc, const float* qg_acc,
-                                const float* as_acc, const float* adx_acc, const double* fbar_sum, long num_params,
+                                const float* as_acc, const float* adx_acc, const double* fbar_sum, const float* tail, long num_params,
                                 float* grads, float scale, cudaStream_t stream);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                         int step, cudaStream_t stream);
@@ -40,6 +46,8 @@ cudaError_t launch_mc_classify(const float* sdf, int nx, int ny, int nz, uint8_t
 cudaError_t launch_mc_edge_vertices(const float* sdf, int nx, int ny, int nz, const long* cells, long n_cells, float sx, float sy, float sz,
                                     float* verts, unsigned short* mask, cudaStream_t stream);
 long compact_num_blocks(long n);
+cudaError_t launch_octree_refine_dev(const uint8_t* flags, uint64_t* keys, const int64_t* lvl, int64_t* lvl_next, long* scratch,
+                                     long level_capacity, long capacity, int* overflow, cudaStream_t stream);
 cudaError_t launch_count_flags(const uint8_t* v, long n, int mode, long* total, long* scratch, cudaStream_t stream);
 cudaError_t launch_compact(const uint8_t* v, long n, int mode, const uint64_t* keys, long* out_idx, uint64_t* out_keys,
                            long* total, long* scratch, cudaStream_t stream);
@@ -85,6 +93,19 @@ struct GradLayout {
 };
 }  // namespace sdf
 
+constexpr size_t kGradTail = 32;
+
+// cached work list of the weight-gradient kernels for one (workspace, tile count, order) combination
+struct DwPlan {
+  const void* ws = nullptr;
+  int tiles = -1, so = -1;
+  int n = 0, pair_n = 0, group = 1;
+  DwItem* items_dev = nullptr;
+  DwItem* items_host = nullptr;   // pinned: the upload is a true async copy, no stream synchronisation
+  int* sync = nullptr;
+  uint64_t last_use = 0;
+};
+
 struct sdfnet_handle {
   sdfnet_desc d;
   int H, L, skip, num_sms;
@@ -107,24 +128,21 @@ struct sdfnet_handle {
   // first needed later is packed on demand from the parameter pointers of the last sdfnet_pack_weights call (the
   // caller packs right before launching, so they are current).  Training then packs the pair layout only, inference
   // the single-CTA layout only.
-  std::vector<const float*> Wptr;
+  std::vector<const float*> Wptr, Bptr;
   bool layout_used[2] = {false, false};
   bool layout_ok[2] = {false, false};
   // gradient accumulators
   float* acc = nullptr;
   size_t acc_floats = 0;
+  float* tail = nullptr;           // kGradTail floats behind the accumulators: (hi, lo) pairs of the 8 loss sums and sum(fbar)
   double* fbar_sum = nullptr;
   GradLayout gl;
-  DwItem* items_dev = nullptr;
-  int* dw_sync = nullptr;          // lock-step counters of the CTA-pair weight-gradient kernel, one per group of items
-  int dw_sync_cap = 0;
-  int dw_group = 1;                // items per group (the blocks of one layer and tile range that share operand tiles)
-  int items_cap = 0;
-  int items_n = 0;                 // cached work list: valid for (items_ws, items_tiles, items_so)
-  int items_pair_n = 0;            // the first items_pair_n entries are 256 x 256 blocks for the CTA-pair kernel
-  const void* items_ws = nullptr;
-  int items_tiles = -1;
-  int items_so = -1;
+  // work lists of the weight-gradient kernels, cached per (workspace, tile count, order): a ragged last batch of an
+  // epoch alternates with the full batches without any rebuild, synchronisation or pageable copy
+  std::vector<DwPlan> plans;
+  uint64_t plan_clock = 0;
+  long* oct_scratch = nullptr;     // block counts of the device-side octree compaction
+  long oct_scratch_cap = 0;
   // instrumentation: kernels launched through this handle, and (when enabled) CUDA-event timing per kernel class
   int64_t launches = 0;
   bool prof_on = false;
@@ -173,6 +191,8 @@ static StepImage make_image(int N, int K16total, int kchunk_k16, bool split, uin
   return s;
 }
 
+static int init_handle(sdfnet_handle* h, const sdfnet_desc* desc, int num_sms);
+
 extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   if (!desc || !out) return fail(1, "sdfnet_create: null argument");
   if (desc->d_in != 3) return fail(1, "sdfnet_create: d_in must be 3 (got %d)", desc->d_in);
@@ -195,6 +215,16 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
 
   sdfnet_handle* h = new (std::nothrow) sdfnet_handle();
   if (!h) return fail(2, "sdfnet_create: out of host memory");
+  const int rc = init_handle(h, desc, prop.multiProcessorCount);
+  if (rc) {
+    sdfnet_destroy(h);  // releases whatever was allocated before the failure
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+static int init_handle(sdfnet_handle* h, const sdfnet_desc* desc, int num_sms) {
   h->d = *desc;
   h->H = desc->hidden;
   h->L = desc->num_hidden;
@@ -210,7 +240,7 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
     h->pair_train = can && !(e && e[0] == '0');
     h->pair_infer = can && !(e && (e[0] == '0' || e[0] == 't'));
   }
-  h->num_sms = prop.multiProcessorCount;
+  h->num_sms = num_sms;
   const int H = h->H, L = h->L;
   uint32_t off = 0;
   const bool sp = h->parity;
@@ -233,7 +263,8 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
   const size_t n_main = static_cast<size_t>(L - 1) * H * H;
   const size_t n_zx = static_cast<size_t>(L) * 16 * H;
   h->acc_floats = n_main + n_zx + 3 * 16 * static_cast<size_t>(H);
-  CU(cudaMalloc(&h->acc, sizeof(float) * h->acc_floats));
+  CU(cudaMalloc(&h->acc, sizeof(float) * (h->acc_floats + kGradTail)));
+  h->tail = h->acc + h->acc_floats;
   CU(cudaMalloc(&h->fbar_sum, sizeof(double)));
   CU(cudaMalloc(&h->scale_dev, 2 * sizeof(float)));
   CU(cudaMalloc(&h->absmax_dev, sizeof(unsigned)));
@@ -242,7 +273,7 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
     const float one[2] = {1.f, 1.f};
     CU(cudaMemcpy(h->scale_dev, one, sizeof(one), cudaMemcpyHostToDevice));
   }
-  CU(cudaMemset(h->acc, 0, sizeof(float) * h->acc_floats));
+  CU(cudaMemset(h->acc, 0, sizeof(float) * (h->acc_floats + kGradTail)));
   CU(cudaMemset(h->fbar_sum, 0, sizeof(double)));
   GradLayout& gl = h->gl;
   gl.H = H; gl.L = L; gl.skip = h->skip;
@@ -259,7 +290,6 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
     np += static_cast<int64_t>(outd) * in + outd;
   }
   gl.num_params = np;
-  *out = h;
   return 0;
 }
 
@@ -272,8 +302,12 @@ extern "C" int sdfnet_destroy(sdfnet_t h) {
   cudaFree(h->fbar_sum);
   cudaFree(h->scale_dev);
   cudaFree(h->absmax_dev);
-  cudaFree(h->items_dev);
-  cudaFree(h->dw_sync);
+  cudaFree(h->oct_scratch);
+  for (auto& pl : h->plans) {
+    cudaFree(pl.items_dev);
+    cudaFreeHost(pl.items_host);
+    cudaFree(pl.sync);
+  }
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   delete h;
@@ -287,29 +321,61 @@ static int out_dim_of(const sdfnet_handle* h, int l) {
   return (h->skip > 0 && l + 1 == h->skip) ? h->H - 3 : h->H;
 }
 
-// pack one weight layout (0 = single CTA, 1 = CTA pair) from the parameter pointers of the last sdfnet_pack_weights call
-static int pack_layout(sdfnet_t h, int layout, cudaStream_t stream) {
+// pack one weight layout (0 = single CTA, 1 = CTA pair) from the parameter pointers of the last sdfnet_pack_weights call:
+// ONE launch for all 2L + 1 step images (+ the bias rows and the last-layer vector when with_bias)
+static int pack_layout(sdfnet_t h, int layout, bool with_bias, cudaStream_t stream) {
   const int H = h->H, L = h->L, dt = h->d.dtype;
   const float c = static_cast<float>(1.0 / std::sqrt(2.0));
   const std::vector<StepImage>& F = layout ? h->Fp : h->F;
   const std::vector<StepImage>& R = layout ? h->Rp : h->R;
-  const int split_ctas = layout ? 2 : 1;
   const float* const* W = h->Wptr.data();
-  Launch lp(h, PC_OTHER, stream, 2 * L + 1);
-  for (int l = 0; l <= L; ++l) {
-    const StepImage& s = F[l];
-    const int kind = l == 0 ? PK_F0 : (l == L ? PK_FL : PK_FH);
-    const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
-    CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           kind, scale, dt, s.split, split_ctas, stream));
+  PackAll pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.H = H; pa.L = L; pa.dtype = dt; pa.halves = layout ? 2 : 1;
+  auto add = [&](const StepImage& s, int l, int kind) {
+    PackImg& im = pa.img[pa.n_img++];
+    im.W = W[l];
+    im.dst = reinterpret_cast<uint16_t*>(h->wpack + s.off);
+    im.out_dim = out_dim_of(h, l); im.in_dim = l == 0 ? 3 : H;
+    im.n_groups = s.n_groups; im.ng = s.ng; im.kchunks = s.kchunks; im.k16 = s.k16; im.kind = kind; im.split = s.split;
+    im.scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
+    im.total = static_cast<long>(s.n_groups) * s.kchunks * (2 * s.k16) * s.ng * 8;
+  };
+  for (int l = 0; l <= L; ++l) add(F[l], l, l == 0 ? PK_F0 : (l == L ? PK_FL : PK_FH));
+  for (int l = L - 1; l >= 0; --l) add(R[l], l, l == 0 ? PK_R0 : PK_RH);
+  if (with_bias) {
+    for (int l = 0; l <= L; ++l) { pa.b[l] = h->Bptr[l]; pa.b_out[l] = out_dim_of(h, l); }
+    pa.bias_dst = h->bias; pa.w_last_dst = h->w_last; pa.w_last_src = W[L];
   }
-  for (int l = L - 1; l >= 0; --l) {
-    const StepImage& s = R[l];
-    const float scale = (h->skip > 0 && l == h->skip) ? c : 1.f;
-    CU(launch_pack_weights(W[l], out_dim_of(h, l), l == 0 ? 3 : H, h->wpack + s.off, s.n_groups, s.ng, s.kchunks, s.k16,
-                           l == 0 ? PK_R0 : PK_RH, scale, dt, s.split, split_ctas, stream));
-  }
+  Launch lp(h, PC_OTHER, stream, 1);
+  CU(launch_pack_all(pa, stream));
   h->layout_ok[layout] = true;
+  return 0;
+}
+// biases + last-layer vector only (no weight layout in use yet)
+static int pack_bias_only(sdfnet_t h, cudaStream_t stream) {
+  PackAll pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.H = h->H; pa.L = h->L; pa.dtype = h->d.dtype; pa.halves = 1;
+  for (int l = 0; l <= h->L; ++l) { pa.b[l] = h->Bptr[l]; pa.b_out[l] = out_dim_of(h, l); }
+  pa.bias_dst = h->bias; pa.w_last_dst = h->w_last; pa.w_last_src = h->Wptr[h->L];
+  Launch lp(h, PC_OTHER, stream, 1);
+  CU(launch_pack_all(pa, stream));
+  return 0;
+}
+// re-pack everything in use from the recorded parameter pointers (sdfnet_pack_weights, sdfnet_fused_adam_step)
+static int repack(sdfnet_t h, cudaStream_t stream) {
+  const bool both = !h->Fp.empty();
+  bool bias_done = false;
+  for (int layout = 0; layout < 2; ++layout) {
+    h->layout_ok[layout] = false;
+    if (layout == 1 && !both) continue;
+    if (h->layout_used[layout]) {
+      if (int rc = pack_layout(h, layout, !bias_done, stream)) return rc;
+      bias_done = true;
+    }
+  }
+  if (!bias_done) return pack_bias_only(h, stream);
   return 0;
 }
 // called by every chain launch site: the layout its program was built on must hold the current weights
@@ -318,31 +384,18 @@ static int ensure_layout(sdfnet_t h, bool pr, cudaStream_t stream) {
   h->layout_used[layout] = true;
   if (h->layout_ok[layout]) return 0;
   if (h->Wptr.empty()) return fail(1, "sdfnet: sdfnet_pack_weights has not been called");
-  return pack_layout(h, layout, stream);
+  return pack_layout(h, layout, false, stream);
 }
 
 extern "C" int sdfnet_pack_weights(sdfnet_t h, const float* const* W, const float* const* b, void* stream_) {
   if (!h || !W || !b) return fail(1, "sdfnet_pack_weights: null argument");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int H = h->H, L = h->L;
-  const bool both = !h->Fp.empty();
+  const int L = h->L;
   for (int l = 0; l <= L; ++l)
     if (!W[l] || !b[l]) return fail(1, "sdfnet_pack_weights: null parameter pointer for layer %d", l);
-  {
-    Launch lp(h, PC_OTHER, stream, L + 1);
-    for (int l = 0; l <= L; ++l) CU(launch_pack_bias(b[l], out_dim_of(h, l), h->bias + static_cast<size_t>(l) * H, H, stream));
-  }
   h->Wptr.assign(W, W + L + 1);
-  for (int layout = 0; layout < 2; ++layout) {
-    h->layout_ok[layout] = false;
-    if (layout == 1 && !both) continue;
-    if (h->layout_used[layout]) {
-      const int rc = pack_layout(h, layout, stream);
-      if (rc) return rc;
-    }
-  }
-  CU(cudaMemcpyAsync(h->w_last, W[L], sizeof(float) * H, cudaMemcpyDeviceToDevice, stream));
-  return 0;
+  h->Bptr.assign(b, b + L + 1);
+  return repack(h, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -523,6 +576,46 @@ extern "C" int sdfnet_octree_level(sdfnet_t h, const uint64_t* keys, int64_t cou
   return 0;
 }
 
+extern "C" int sdfnet_octree_levels(sdfnet_t h, int32_t level_lo, int32_t level_hi, int32_t uni_level, float band, uint64_t* keys,
+                                    float* sdf, uint8_t* flags, int64_t capacity, int64_t* level_table, int32_t* overflow,
+                                    void* stream_) {
+  if (!h || !keys || !sdf || !flags || !level_table || !overflow) return fail(1, "sdfnet_octree_levels: null argument");
+  if (level_lo < 0 || level_hi > 20 || level_lo > level_hi) return fail(1, "sdfnet_octree_levels: levels [%d,%d] outside [0,20]", level_lo, level_hi);
+  if (capacity <= 0 || capacity > (static_cast<int64_t>(1) << 30)) return fail(1, "sdfnet_octree_levels: capacity must be in (0, 2^30]");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long need = compact_num_blocks(capacity) + 2;
+  if (need > h->oct_scratch_cap) {
+    CU(cudaStreamSynchronize(stream));
+    cudaFree(h->oct_scratch);
+    h->oct_scratch = nullptr;
+    h->oct_scratch_cap = 0;
+    CU(cudaMalloc(&h->oct_scratch, sizeof(long) * need));
+    h->oct_scratch_cap = need;
+  }
+  for (int level = level_lo; level <= level_hi; ++level) {
+    // a level holds at most 8^level cells: bounds the grid of the (device-count driven) launches of the coarse levels
+    int64_t level_cap = capacity;
+    if (3 * level < 40 && (static_cast<int64_t>(1) << (3 * level)) < capacity) level_cap = static_cast<int64_t>(1) << (3 * level);
+    ChainParams p;
+    base_params(h, p);
+    p.src = SRC_OCTREE;
+    p.keys = keys;
+    p.level = level;
+    p.f_out = sdf;
+    p.lvl = level_table + 2 * level;
+    p.flag_out = flags;
+    p.flag_thresh = band * ldexpf(2.f, -level);  // band * h_level, one fp32 rounding (oracle/sdf_oracle.py:octree_flags)
+    p.flag_all = level < uni_level ? 1 : 0;
+    if (int rc = run_forward(h, p, level_cap, stream)) return rc;
+    if (level < level_hi && level >= uni_level) {
+      Launch lf(h, PC_OTHER, stream, 3);
+      CU(launch_octree_refine_dev(flags, keys, level_table + 2 * level, level_table + 2 * (level + 1), h->oct_scratch, level_cap,
+                                  capacity, overflow, stream));
+    }
+  }
+  return 0;
+}
+
 extern "C" int sdfnet_forward_grad(sdfnet_t h, const float* x, int64_t n, float* sdf_out, float* grad_out, void* ws_,
                                    size_t ws_bytes, void* stream) {
   if (!h || !x || !grad_out) return fail(1, "sdfnet_forward_grad: null argument");
@@ -569,15 +662,18 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   const uint32_t ib = img_bytes(H);
   const uint32_t xb = 2 * kGranuleBytes;
   const GradLayout& gl = h->gl;
-  auto launch_both = [&]() -> int {
-    Launch lr(h, PC_DW, stream, h->items_pair_n > 0 && h->items_n > h->items_pair_n ? 2 : 1);
-    if (h->items_pair_n > 0)
-      CU(launch_dw2(h->items_dev, h->items_pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, h->dw_sync, h->dw_group, stream));
-    if (h->items_n > h->items_pair_n)
-      CU(launch_dw(h->items_dev + h->items_pair_n, h->items_n - h->items_pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+  auto launch_plan = [&](DwPlan& pl) -> int {
+    pl.last_use = ++h->plan_clock;
+    Launch lr(h, PC_DW, stream, pl.pair_n > 0 && pl.n > pl.pair_n ? 2 : 1);
+    if (pl.pair_n > 0)
+      CU(launch_dw2(pl.items_dev, pl.pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, pl.sync, pl.group, stream));
+    if (pl.n > pl.pair_n)
+      CU(launch_dw(pl.items_dev + pl.pair_n, pl.n - pl.pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
     return 0;
   };
-  if (h->items_ws == s.A && h->items_tiles == tiles && h->items_so == (second_order ? 1 : 0) && h->items_n > 0) return launch_both();
+  for (auto& pl : h->plans)
+    if (pl.ws == s.A && pl.tiles == tiles && pl.so == (second_order ? 1 : 0) && pl.n > 0) return launch_plan(pl);
+  int dw_group = 1;
   std::vector<DwItem> items;
   const int nmb = H / 128 > 0 ? H / 128 : 1;
   if (H % 128) return fail(1, "training requires hidden width multiple of 128 (got %d)", H);
@@ -593,10 +689,10 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
     const int nb2 = H / 256;
     const int types = (L - 1) * nb2 * nb2;
     int ksplit = (8 * (h->num_sms / 2) + types - 1) / types;
-    h->dw_group = getenv("SDFNET_DW_NOSYNC") ? 1 : nb2 * nb2;
-    if (h->dw_group > 1) {
+    dw_group = getenv("SDFNET_DW_NOSYNC") ? 1 : nb2 * nb2;
+    if (dw_group > 1) {
       // lock-step groups (dw.cu): deal the items over a multiple-of-group number of pairs with no ragged last round
-      const int pairs_eff = (h->num_sms / 2) / h->dw_group * h->dw_group;
+      const int pairs_eff = (h->num_sms / 2) / dw_group * dw_group;
       if (pairs_eff > 0) {
         int a = types, b = pairs_eff;
         while (b) { const int t = a % b; a = b; b = t; }
@@ -686,28 +782,29 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
     }
   }
   const int n_items = static_cast<int>(items.size());
-  if (n_items > h->items_cap) {
-    CU(cudaStreamSynchronize(stream));  // a previous launch may still read the old list
-    cudaFree(h->items_dev);
-    h->items_dev = nullptr;
-    h->items_cap = 0;
-    CU(cudaMalloc(&h->items_dev, sizeof(DwItem) * n_items));
-    h->items_cap = n_items;
-  }
-  if (pair_n / (h->dw_group > 0 ? h->dw_group : 1) + 1 > h->dw_sync_cap) {
+  // new plan: own device list, pinned host copy (true async upload, no synchronisation), own lock-step counters.  The
+  // cache holds a few plans (full batch, ragged last batch, first / second order); the least recently used one is
+  // recycled only after the stream has drained (a launch may still read it) -- not in steady state.
+  DwPlan* pl = nullptr;
+  constexpr size_t kMaxPlans = 16;
+  if (h->plans.size() < kMaxPlans) {
+    h->plans.emplace_back();
+    pl = &h->plans.back();
+  } else {
+    pl = &h->plans[0];
+    for (auto& q : h->plans) if (q.last_use < pl->last_use) pl = &q;
     CU(cudaStreamSynchronize(stream));
-    cudaFree(h->dw_sync);
-    h->dw_sync = nullptr;
-    h->dw_sync_cap = 0;
-    const int need = pair_n + 64;
-    CU(cudaMalloc(&h->dw_sync, sizeof(int) * need));
-    h->dw_sync_cap = need;
+    cudaFree(pl->items_dev); cudaFreeHost(pl->items_host); cudaFree(pl->sync);
+    *pl = DwPlan();
   }
-  // the list is rebuilt per call from a pageable host vector: a synchronous copy keeps it simple and safe
-  CU(cudaMemcpyAsync(h->items_dev, items.data(), sizeof(DwItem) * n_items, cudaMemcpyHostToDevice, stream));
-  CU(cudaStreamSynchronize(stream));
-  h->items_n = n_items; h->items_pair_n = pair_n; h->items_ws = s.A; h->items_tiles = tiles; h->items_so = second_order ? 1 : 0;
-  return launch_both();
+  CU(cudaMalloc(&pl->items_dev, sizeof(DwItem) * n_items));
+  CU(cudaMallocHost(&pl->items_host, sizeof(DwItem) * n_items));
+  CU(cudaMalloc(&pl->sync, sizeof(int) * (pair_n + 64)));
+  memcpy(pl->items_host, items.data(), sizeof(DwItem) * n_items);
+  CU(cudaMemcpyAsync(pl->items_dev, pl->items_host, sizeof(DwItem) * n_items, cudaMemcpyHostToDevice, stream));
+  pl->ws = s.A; pl->tiles = tiles; pl->so = second_order ? 1 : 0;
+  pl->n = n_items; pl->pair_n = pair_n; pl->group = dw_group;
+  return launch_plan(*pl);
 }
 
 // forward (+reverse) over one chunk, spilling what training needs
@@ -760,7 +857,7 @@ int64_t chunk_points(sdfnet_t h, size_t ws_bytes) {
 
 extern "C" int sdfnet_zero_grads(sdfnet_t h, void* stream) {
   if (!h) return fail(1, "sdfnet_zero_grads: null handle");
-  CU(cudaMemsetAsync(h->acc, 0, sizeof(float) * h->acc_floats, static_cast<cudaStream_t>(stream)));
+  CU(cudaMemsetAsync(h->acc, 0, sizeof(float) * (h->acc_floats + kGradTail), static_cast<cudaStream_t>(stream)));
   CU(cudaMemsetAsync(h->fbar_sum, 0, sizeof(double), static_cast<cudaStream_t>(stream)));
   return 0;
 }
@@ -769,7 +866,7 @@ extern "C" int sdfnet_read_grads(sdfnet_t h, float* grads, float scale, void* st
   if (!h || !grads) return fail(1, "sdfnet_read_grads: null argument");
   const GradLayout& gl = h->gl;
   Launch lr(h, PC_OTHER, static_cast<cudaStream_t>(stream));
-  CU(launch_unpack_grads(gl.H, gl.L, gl.skip, gl.main_acc, gl.zx_acc, gl.qg_acc, gl.as_acc, gl.adx_acc, gl.fbar_sum,
+  CU(launch_unpack_grads(gl.H, gl.L, gl.skip, gl.main_acc, gl.zx_acc, gl.qg_acc, gl.as_acc, gl.adx_acc, gl.fbar_sum, h->tail,
                          gl.num_params, grads, scale, static_cast<cudaStream_t>(stream)));
   return 0;
 }
@@ -803,7 +900,7 @@ extern "C" int sdfnet_backward(sdfnet_t h, const float* x, int64_t n, const floa
       Launch ls(h, PC_OTHER, stream, 2 + (fb ? 1 : 0) + (gb ? 1 : 0));
       if (fb) CU(launch_absmax(fb, m, h->absmax_dev, stream));
       if (gb) CU(launch_absmax(gb, 3 * m, h->absmax_dev, stream));
-      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, nullptr, h->fbar_sum, h->tail, stream));
     }
     if (int rc = run_ta(h, m, s, fb, gb, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, gbar != nullptr, stream)) return rc;
@@ -815,7 +912,7 @@ extern "C" int sdfnet_train_step_igr(sdfnet_t h, const float* x, const float* y,
                                      double* loss_sums, void* ws_, size_t ws_bytes, void* stream_) {
   if (!h || !x || !y || !cfg || !loss_sums) return fail(1, "sdfnet_train_step_igr: null argument");
   if (n <= 0) return 0;
-  if (cfg->n_global <= 0) return fail(1, "sdfnet_train_step_igr: n_global must be positive");
+  if (cfg->n_global <= 0 && !cfg->label_stats_dev) return fail(1, "sdfnet_train_step_igr: n_global must be positive (or label_stats_dev given)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   uint8_t* ws = align_ws(ws_, ws_bytes);
   const int64_t chunk = ws_ ? chunk_points(h, ws_bytes) : 0;
@@ -827,11 +924,12 @@ extern "C" int sdfnet_train_step_igr(sdfnet_t h, const float* x, const float* y,
     carve(h, 1, ws, tiles, s);
     if (int rc = run_fg(h, x + o * 3, m, s, true, stream)) return rc;
     {
-      Launch ls(h, PC_OTHER, stream, 3);
+      Launch ls(h, PC_OTHER, stream, 2);
       CU(launch_igr_seeds(s.f, s.g, y + o * 4, m, cfg->delta, cfg->tau, cfg->lambda_g, cfg->regularizer_threshold,
-                          cfg->mean_t, cfg->mean_t_dev, 1.0 / static_cast<double>(cfg->n_global), cfg->data_term, h->relu ? 1 : 0,
+                          cfg->mean_t, cfg->mean_t_dev, cfg->label_stats_dev, cfg->n_global > 0 ? 1.0 / static_cast<double>(cfg->n_global) : 0.0,
+                          cfg->data_term, h->relu ? 1 : 0,
                           h->absmax_dev, s.fbar, s.gbar, loss_sums, h->fbar_sum, stream));
-      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, loss_sums, h->fbar_sum, h->tail, stream));
     }
     if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, true, stream)) return rc;
@@ -855,10 +953,10 @@ extern "C" int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int6
     carve(h, 1, ws, tiles, s);
     if (int rc = run_fg(h, x + o * 3, m, s, false, stream)) return rc;
     {
-      Launch ls(h, PC_OTHER, stream, 3);
+      Launch ls(h, PC_OTHER, stream, 2);
       CU(launch_pcd_seeds(s.f, nullptr, m, 0, 1.f / static_cast<float>(n_global), h->relu ? 1 : 0, h->absmax_dev, s.fbar,
                           nullptr, loss_sums, h->fbar_sum, stream));
-      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, loss_sums, h->fbar_sum, h->tail, stream));
     }
     if (int rc = run_ta(h, m, s, s.fbar, nullptr, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, false, stream)) return rc;
@@ -871,15 +969,61 @@ extern "C" int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int6
     carve(h, 1, ws, tiles, s);
     if (int rc = run_fg(h, xp + o * 3, m, s, true, stream)) return rc;
     {
-      Launch ls(h, PC_OTHER, stream, 3);
+      Launch ls(h, PC_OTHER, stream, 2);
       CU(launch_pcd_seeds(s.f, s.g, m, 1, lambda_g / static_cast<float>(m_global), h->relu ? 1 : 0, h->absmax_dev, s.fbar,
                           s.gbar, loss_sums, h->fbar_sum, stream));
-      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, loss_sums, h->fbar_sum, h->tail, stream));
     }
     if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, true, stream)) return rc;
   }
   return 0;
+}
+
+extern "C" int sdfnet_label_stats(const float* y, int64_t n, float delta, double* out2, void* stream_) {
+  if (!y || !out2) return fail(1, "sdfnet_label_stats: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CU(cudaMemsetAsync(out2, 0, 2 * sizeof(double), stream));
+  if (n > 0) CU(launch_label_stats(y, n, delta, out2, stream));
+  return 0;
+}
+
+extern "C" int sdfnet_grad_buffer(sdfnet_t h, float** buf, int64_t* n_floats) {
+  if (!h || !buf || !n_floats) return fail(1, "sdfnet_grad_buffer: null argument");
+  *buf = h->acc;
+  *n_floats = static_cast<int64_t>(h->acc_floats + kGradTail);
+  return 0;
+}
+
+extern "C" int sdfnet_loss_value(sdfnet_t h, int32_t kind, float tau, float lambda_g, int32_t data_term, int64_t n_global,
+                                 int64_t m_global, float* out4, void* stream) {
+  if (!h || !out4) return fail(1, "sdfnet_loss_value: null argument");
+  if (kind != 0 && kind != 1) return fail(1, "sdfnet_loss_value: kind must be 0 (IGRLOSS) or 1 (point cloud)");
+  Launch ll(h, PC_OTHER, static_cast<cudaStream_t>(stream));
+  CU(launch_loss_value(h->tail, kind, tau, lambda_g, data_term, n_global > 0 ? 1.0 / static_cast<double>(n_global) : 0.0,
+                       m_global > 0 ? 1.0 / static_cast<double>(m_global) : 0.0, out4, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int sdfnet_fused_adam_step(sdfnet_t h, float* const* W, float* const* b, float* exp_avg, float* exp_avg_sq, float lr,
+                                      float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                                      const float* grad_scale_dev, float* grads_out, void* stream_) {
+  if (!h || !W || !b || !exp_avg || !exp_avg_sq) return fail(1, "sdfnet_fused_adam_step: null argument");
+  if (step < 1) return fail(1, "sdfnet_fused_adam_step: step counts from 1");
+  for (int l = 0; l <= h->L; ++l)
+    if (!W[l] || !b[l]) return fail(1, "sdfnet_fused_adam_step: null parameter pointer for layer %d", l);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const GradLayout& gl = h->gl;
+  {
+    Launch la(h, PC_OTHER, stream);
+    CU(launch_fused_adam(gl.H, gl.L, gl.skip, gl.main_acc, gl.zx_acc, gl.qg_acc, gl.as_acc, gl.adx_acc, gl.fbar_sum, h->tail,
+                         gl.num_params, W, b, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale, grad_scale_dev,
+                         grads_out, stream));
+  }
+  // the updated parameters become the packed operand images of the next step
+  h->Wptr.assign(W, W + h->L + 1);
+  h->Bptr.assign(b, b + h->L + 1);
+  return repack(h, stream);
 }
 
 extern "C" int64_t sdfnet_launch_count(sdfnet_t h) { return h ? h->launches : -1; }

@@ -29,73 +29,7 @@ __device__ __forceinline__ uint16_t bits16(float v, int dtype) {
 enum : int { PK_F0 = 0, PK_FH = 1, PK_FL = 2, PK_RH = 3, PK_R0 = 4 };
 
 // split != 0 (parity mode): kchunks counts hi chunks followed by lo chunks, lo = rnd16(v - rnd16(v)).
-__global__ void pack_weights_kernel(const float* __restrict__ W, int out_dim, int in_dim, uint16_t* __restrict__ dst,
-                                    int n_groups, int ng, int kchunks, int k16, int kind, float scale, int dtype, int split,
-                                    int halves) {
-  const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
-  const int hrows = ng / halves;
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    long t = idx;
-    const int e = static_cast<int>(t % 8); t /= 8;
-    const int row = static_cast<int>(t % hrows); t /= hrows;
-    const int gr = static_cast<int>(t % (2 * k16)); t /= (2 * k16);
-    const int hf = static_cast<int>(t % halves); t /= halves;
-    int kc = static_cast<int>(t % kchunks); t /= kchunks;
-    const int g = static_cast<int>(t);
-    const int n = g * ng + hf * hrows + row;
-    bool lo_part = false;
-    if (split) {
-      lo_part = kc >= kchunks / 2;
-      kc %= kchunks / 2;
-    }
-    const int k = (kc * 2 * k16 + gr) * 8 + e;
-    float v = 0.f;
-    switch (kind) {
-      case PK_F0: {  // layer 0 forward: W [H][3] against the split input block
-        if (n < out_dim && k < 15) {
-          const float w = W[n * in_dim + (k % 3)];
-          const float hi = rnd16(w, dtype);
-          v = (k < 9) ? hi : rnd16(w - hi, dtype);
-        }
-      } break;
-      case PK_FH:
-        if (n < out_dim && k < in_dim) v = scale * W[static_cast<long>(n) * in_dim + k];
-        break;
-      case PK_FL:
-        if (n == 0 && k < in_dim) v = W[k];
-        break;
-      case PK_RH:  // B[n = input feature][k = output feature]
-        if (k < out_dim && n < in_dim) v = scale * W[static_cast<long>(k) * in_dim + n];
-        break;
-      case PK_R0:  // W_0 [H][3] transposed: n = coordinate, k = feature
-        if (n < in_dim && k < out_dim) v = W[k * in_dim + n];
-        break;
-    }
-    if (lo_part) v = v - rnd16(v, dtype);
-    dst[idx] = bits16(v, dtype);
-  }
-}
-
-__global__ void pack_bias_kernel(const float* __restrict__ b, int out_dim, float* __restrict__ dst, int H) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x) dst[i] = i < out_dim ? b[i] : 0.f;
-}
-
-cudaError_t launch_pack_weights(const float* W, int out_dim, int in_dim, void* dst, int n_groups, int ng, int kchunks,
-                                int k16, int kind, float scale, int dtype, int split, int halves, cudaStream_t stream) {
-  const long total = static_cast<long>(n_groups) * kchunks * (2 * k16) * ng * 8;
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > 1184) blocks = 1184;
-  if (blocks < 1) blocks = 1;
-  pack_weights_kernel<<<blocks, 256, 0, stream>>>(W, out_dim, in_dim, static_cast<uint16_t*>(dst), n_groups, ng, kchunks,
-                                                  k16, kind, scale, dtype, split, halves);
-  return cudaGetLastError();
-}
-cudaError_t launch_pack_bias(const float* b, int out_dim, float* dst, int H, cudaStream_t stream) {
-  pack_bias_kernel<<<(H + 255) / 256, 256, 0, stream>>>(b, out_dim, dst, H);
-  return cudaGetLastError();
-}
-
+// (kernel: pack_all_kernel below, one launch per layout)
 
 // ------------------------------------------------------------------------------------------------
 // Loss seeds.  Per point: (f, g) -> (fbar, gbar) = dL/df, dL/dg and the partial sums of the loss terms.
@@ -132,6 +66,7 @@ struct IgrCfgDev {
   float delta, tau, lambda_g, thr, mean_t, inv_n;
   int data_term, relu_tanh;
   const float* mean_t_dev;
+  const double* stats_dev;   // {sum clamp(S), N} over the whole (multi-GPU) batch: overrides mean_t and inv_n
   unsigned* absmax;   // running max |seed| (float bits; non-negative floats order like unsigned ints)
 };
 
@@ -147,10 +82,16 @@ __device__ __forceinline__ void block_absmax(float m, unsigned* absmax) {
 //   L = D + tau mean(reg) + lambda mean(eik),  D = mean(p^2)+mean(t^2)-2 mean(p) mean(t)  |  mean((p-t)^2)
 __global__ void igr_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ y,
                                  long n, IgrCfgDev c, float* __restrict__ fbar, float* __restrict__ gbar,
-                                 double* __restrict__ sums) {
+                                 double* __restrict__ sums, double* __restrict__ fbar_sum) {
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float fsum[1] = {0.f};
   float amax = 0.f;
   if (c.mean_t_dev) c.mean_t = __ldg(c.mean_t_dev);
+  if (c.stats_dev) {
+    const double st = c.stats_dev[0], nn = c.stats_dev[1];
+    c.mean_t = static_cast<float>(st / nn);
+    c.inv_n = static_cast<float>(1.0 / nn);
+  }
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float fi = f[i];
     const float gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
@@ -190,19 +131,23 @@ __global__ void igr_seeds_kernel(const float* __restrict__ f, const float* __res
       bx *= d; by *= d; bz *= d;
     }
     fbar[i] = fb;
+    fsum[0] += fb;
     gbar[3 * i] = bx; gbar[3 * i + 1] = by; gbar[3 * i + 2] = bz;
     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(fb), fabsf(bx)), fmaxf(fabsf(by), fabsf(bz))));
   }
   block_absmax(amax, c.absmax);
   block_accumulate<8>(acc, sums);
+  __syncthreads();
+  block_accumulate<1>(fsum, fbar_sum);  // sum fbar = d L / d b_L
 }
 
 // reference executor/executordistributed.py:73-79:  which = 0: surface points, L += mean |f|  (fbar = sign(f)/N);
 // which = 1: perturbed points, L += lambda mean (|g|-1)^2  (gbar = (lambda/M) 2 (|g|-1) g/|g|).  coef = 1/N or lambda/M.
 __global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, long n, int which, float coef,
                                  int relu_tanh, unsigned* __restrict__ absmax, float* __restrict__ fbar, float* __restrict__ gbar,
-                                 double* __restrict__ sums) {
+                                 double* __restrict__ sums, double* __restrict__ fbar_sum) {
   float acc[1] = {0.f};
+  float fsum[1] = {0.f};
   float amax = 0.f;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float fi = f[i];
@@ -224,17 +169,31 @@ __global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __res
       bx *= d; by *= d; bz *= d;
     }
     fbar[i] = fb;
+    fsum[0] += fb;
     if (gbar) { gbar[3 * i] = bx; gbar[3 * i + 1] = by; gbar[3 * i + 2] = bz; }
     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(fb), fabsf(bx)), fmaxf(fabsf(by), fabsf(bz))));
   }
   block_absmax(amax, absmax);
   block_accumulate<1>(acc, sums + which);
+  __syncthreads();
+  block_accumulate<1>(fsum, fbar_sum);
 }
 
 __global__ void sum_kernel(const float* __restrict__ v, long n, double* __restrict__ out) {
   float acc[1] = {0.f};
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) acc[0] += v[i];
   block_accumulate<1>(acc, out);
+}
+
+// {sum clamp(y[:,0], +-delta), count} of one shard's labels (y [n,4]; model/losses.py:115): what the pairwise data term and
+// the loss normaliser need from the whole batch before any seed can be formed
+__global__ void label_stats_kernel(const float* __restrict__ y, long n, float delta, double* __restrict__ out2) {
+  float acc[2] = {0.f, 0.f};
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    acc[0] += fminf(fmaxf(__ldg(y + 4 * i), -delta), delta);
+    acc[1] += 1.f;
+  }
+  block_accumulate<2>(acc, out2);
 }
 
 static int seed_blocks(long n) {
@@ -245,23 +204,26 @@ static int seed_blocks(long n) {
 }
 
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
-                             float lambda_g, float thr, float mean_t, const float* mean_t_dev, double inv_n, int data_term,
-                             int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
-                             cudaStream_t stream) {
+                             float lambda_g, float thr, float mean_t, const float* mean_t_dev, const double* stats_dev, double inv_n,
+                             int data_term, int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums,
+                             double* fbar_sum, cudaStream_t stream) {
   IgrCfgDev c;
   c.mean_t_dev = mean_t_dev;
+  c.stats_dev = stats_dev;
   c.absmax = absmax;
   c.delta = delta; c.tau = tau; c.lambda_g = lambda_g; c.thr = thr; c.mean_t = mean_t;
   c.inv_n = static_cast<float>(inv_n); c.data_term = data_term; c.relu_tanh = relu_tanh;
-  igr_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, y, n, c, fbar, gbar, sums);
-  sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(fbar, n, fbar_sum);
+  igr_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, y, n, c, fbar, gbar, sums, fbar_sum);
+  return cudaGetLastError();
+}
+cudaError_t launch_label_stats(const float* y, int64_t n, float delta, double* out2, cudaStream_t stream) {
+  label_stats_kernel<<<seed_blocks(n), 256, 0, stream>>>(y, n, delta, out2);
   return cudaGetLastError();
 }
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
                              unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
                              cudaStream_t stream) {
-  pcd_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, n, which, coef, relu_tanh, absmax, fbar, gbar, sums);
-  sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(fbar, n, fbar_sum);
+  pcd_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, n, which, coef, relu_tanh, absmax, fbar, gbar, sums, fbar_sum);
   return cudaGetLastError();
 }
 // ReLU/tanh network: turn seeds w.r.t. (f = tanh z, g = (1-f^2) G) into seeds w.r.t. (z, G), see igr_seeds_kernel.
@@ -291,7 +253,18 @@ __global__ void absmax_kernel(const float* __restrict__ v, long n, unsigned* __r
   block_absmax(m, absmax);
 }
 // scale[0] = 2^-ceil(log2(absmax)) (largest seed lands in (0.5, 1]), scale[1] = 1 / scale[0]; absmax is reset
-__global__ void seed_scale_kernel(unsigned* __restrict__ absmax, float* __restrict__ scale) {
+// It also mirrors the running double-precision loss sums and sum(fbar) as (hi, lo) float pairs into the tail of the
+// gradient buffer, so that ONE fp32 sum-allreduce over [accumulators | tail] carries gradients and loss sums.
+__global__ void seed_scale_kernel(unsigned* __restrict__ absmax, float* __restrict__ scale, const double* __restrict__ sums,
+                                  const double* __restrict__ fbar_sum, float* __restrict__ tail) {
+  if (tail) {
+    for (int i = 0; i < 9; ++i) {
+      const double d = i < 8 ? (sums ? sums[i] : 0.0) : *fbar_sum;
+      const float hi = static_cast<float>(d);
+      tail[2 * i] = hi;
+      tail[2 * i + 1] = static_cast<float>(d - static_cast<double>(hi));
+    }
+  }
   const float m = __uint_as_float(*absmax);
   int e = 0;
   float mult = 1.f;
@@ -308,8 +281,9 @@ cudaError_t launch_absmax(const float* v, int64_t n, unsigned* absmax, cudaStrea
   absmax_kernel<<<seed_blocks(n), 256, 0, stream>>>(v, n, absmax);
   return cudaGetLastError();
 }
-cudaError_t launch_seed_scale(unsigned* absmax, float* scale, cudaStream_t stream) {
-  seed_scale_kernel<<<1, 1, 0, stream>>>(absmax, scale);
+cudaError_t launch_seed_scale(unsigned* absmax, float* scale, const double* sums, const double* fbar_sum, float* tail,
+                              cudaStream_t stream) {
+  seed_scale_kernel<<<1, 1, 0, stream>>>(absmax, scale, sums, fbar_sum, tail);
   return cudaGetLastError();
 }
 cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream) {
@@ -327,47 +301,22 @@ struct GradLayoutDev {
   const double* fbar_sum;
 };
 
-__global__ void unpack_grads_kernel(GradLayoutDev gl, float* __restrict__ grads, long num_params, float scale) {
-  const int H = gl.H, L = gl.L;
-  const float c = 0.70710678118654752440f;
+__device__ __forceinline__ float unpack_one(const GradLayoutDev& gl, const float* tail, long idx, int& layer, int& is_bias, long& off);
+
+__global__ void unpack_grads_kernel(GradLayoutDev gl, const float* __restrict__ tail, float* __restrict__ grads, long num_params,
+                                    float scale) {
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < num_params; idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    long rem = idx;
-    float v = 0.f;
-    for (int l = 0; l <= L; ++l) {
-      const int in = l == 0 ? 3 : H;
-      const int outd = l == L ? 1 : ((gl.skip > 0 && l + 1 == gl.skip) ? H - 3 : H);
-      const long wsz = static_cast<long>(outd) * in;
-      if (rem < wsz) {
-        const int m = static_cast<int>(rem / in), n = static_cast<int>(rem % in);
-        if (l == 0) {
-          const float* zx = gl.zx_acc;  // layer 0 block: [16][H]
-          v = zx[(n) * H + m] + zx[(n + 3) * H + m] + zx[(n + 6) * H + m] + gl.qg_acc[(n) * H + m] +
-              gl.qg_acc[(n + 3) * H + m] + gl.qg_acc[(n + 6) * H + m];
-        } else if (l == L) {
-          v = gl.as_acc[0 * H + n] + gl.as_acc[1 * H + n] + gl.as_acc[2 * H + n] + gl.adx_acc[15 * H + n];
-        } else {
-          v = gl.main_acc[(static_cast<long>(l - 1) * H + n) * H + m];
-          if (gl.skip > 0 && l == gl.skip) v *= c;
-        }
-        break;
-      }
-      rem -= wsz;
-      if (rem < outd) {
-        const int m = static_cast<int>(rem);
-        v = l == L ? static_cast<float>(*gl.fbar_sum) : gl.zx_acc[(static_cast<long>(l) * 16 + 15) * H + m];
-        break;
-      }
-      rem -= outd;
-    }
-    grads[idx] = v * scale;
+    int layer, is_bias;
+    long off;
+    grads[idx] = unpack_one(gl, tail, idx, layer, is_bias, off) * scale;
   }
 }
 
 cudaError_t launch_unpack_grads(int H, int L, int skip, const float* main_acc, const float* zx_acc, const float* qg_acc,
-                                const float* as_acc, const float* adx_acc, const double* fbar_sum, long num_params,
+                                const float* as_acc, const float* adx_acc, const double* fbar_sum, const float* tail, long num_params,
                                 float* grads, float scale, cudaStream_t stream) {
   GradLayoutDev gl{H, L, skip, main_acc, zx_acc, qg_acc, as_acc, adx_acc, fbar_sum};
-  unpack_grads_kernel<<<1184, 256, 0, stream>>>(gl, grads, num_params, scale);
+  unpack_grads_kernel<<<1184, 256, 0, stream>>>(gl, tail, grads, num_params, scale);
   return cudaGetLastError();
 }
 
@@ -394,9 +343,184 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n,
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused optimizer tail (reference executor/executor.py:160,177: Adam over 18 tensors).
+// ONE kernel reads the gradient accumulators (after the optional cross-rank sum), unpacks them into state_dict order,
+// applies torch.optim.Adam's update to the fp32 parameters in place; ONE kernel then re-packs all weight images and the
+// bias / last-layer vectors the next step's programs read.  Replaces unpack_grads + 18 multiplies + foreach Adam + 26
+// pack launches of the generic path.
+// ------------------------------------------------------------------------------------------------
+struct ParamPtrs {
+  float* W[kMaxLayers + 1];
+  float* b[kMaxLayers + 1];
+};
+
+__device__ __forceinline__ float unpack_one(const GradLayoutDev& gl, const float* tail, long idx, int& layer, int& is_bias, long& off) {
+  const int H = gl.H, L = gl.L;
+  const float c = 0.70710678118654752440f;
+  long rem = idx;
+  float v = 0.f;
+  for (int l = 0; l <= L; ++l) {
+    const int in = l == 0 ? 3 : H;
+    const int outd = l == L ? 1 : ((gl.skip > 0 && l + 1 == gl.skip) ? H - 3 : H);
+    const long wsz = static_cast<long>(outd) * in;
+    if (rem < wsz) {
+      const int m = static_cast<int>(rem / in), n = static_cast<int>(rem % in);
+      if (l == 0) {
+        const float* zx = gl.zx_acc;
+        v = zx[(n) * H + m] + zx[(n + 3) * H + m] + zx[(n + 6) * H + m] + gl.qg_acc[(n) * H + m] +
+            gl.qg_acc[(n + 3) * H + m] + gl.qg_acc[(n + 6) * H + m];
+      } else if (l == L) {
+        v = gl.as_acc[0 * H + n] + gl.as_acc[1 * H + n] + gl.as_acc[2 * H + n] + gl.adx_acc[15 * H + n];
+      } else {
+        v = gl.main_acc[(static_cast<long>(l - 1) * H + n) * H + m];
+        if (gl.skip > 0 && l == gl.skip) v *= c;
+      }
+      layer = l; is_bias = 0; off = rem;
+      return v;
+    }
+    rem -= wsz;
+    if (rem < outd) {
+      const int m = static_cast<int>(rem);
+      // d L / d b_L = sum fbar: from the (hi, lo) tail pair when the buffer went through an allreduce, else the double
+      v = l == L ? (tail ? tail[16] + tail[17] : static_cast<float>(*gl.fbar_sum)) : gl.zx_acc[(static_cast<long>(l) * 16 + 15) * H + m];
+      layer = l; is_bias = 1; off = rem;
+      return v;
+    }
+    rem -= outd;
+  }
+  layer = 0; is_bias = 0; off = 0;
+  return 0.f;
+}
+
+__global__ void fused_adam_kernel(GradLayoutDev gl, const float* __restrict__ tail, ParamPtrs pp, float* __restrict__ m,
+                                  float* __restrict__ v, long num_params, float lr_bc1, float b1, float b2, float eps,
+                                  float inv_bc2_sqrt, float scale, const float* __restrict__ scale_dev, float* __restrict__ grads_out) {
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.f);
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < num_params; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    int layer, is_bias;
+    long off;
+    const float gi = unpack_one(gl, tail, idx, layer, is_bias, off) * sc;
+    if (grads_out) grads_out[idx] = gi;
+    float* p = (is_bias ? pp.b[layer] : pp.W[layer]) + off;
+    const float mi = b1 * m[idx] + (1.f - b1) * gi;
+    const float vi = b2 * v[idx] + (1.f - b2) * gi * gi;
+    m[idx] = mi;
+    v[idx] = vi;
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    *p -= lr_bc1 * (mi / denom);
+  }
+}
+
+cudaError_t launch_fused_adam(int H, int L, int skip, const float* main_acc, const float* zx_acc, const float* qg_acc,
+                              const float* as_acc, const float* adx_acc, const double* fbar_sum, const float* tail, long num_params,
+                              float* const* W, float* const* b, float* m, float* v, float lr, float b1, float b2, float eps, int step,
+                              float scale, const float* scale_dev, float* grads_out, cudaStream_t stream) {
+  GradLayoutDev gl{H, L, skip, main_acc, zx_acc, qg_acc, as_acc, adx_acc, fbar_sum};
+  ParamPtrs pp;
+  for (int l = 0; l <= kMaxLayers; ++l) { pp.W[l] = l <= L ? W[l] : nullptr; pp.b[l] = l <= L ? b[l] : nullptr; }
+  // bias corrections in double like torch.optim.Adam (python floats)
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
+  fused_adam_kernel<<<1184, 256, 0, stream>>>(gl, tail, pp, m, v, num_params, static_cast<float>(lr / bc1), b1, b2, eps,
+                                              static_cast<float>(1.0 / sqrt(bc2)), scale, scale_dev, grads_out);
+  return cudaGetLastError();
+}
+
+// All step images of one weight layout + the bias rows + the last-layer vector in ONE launch (PackAll: sdf_internal.h).
+__device__ __forceinline__ void pack_one(const PackImg& im, long idx, int dtype, int halves) {
+  const int hrows = im.ng / halves;
+  long t = idx;
+  const int e = static_cast<int>(t % 8); t /= 8;
+  const int row = static_cast<int>(t % hrows); t /= hrows;
+  const int gr = static_cast<int>(t % (2 * im.k16)); t /= (2 * im.k16);
+  const int hf = static_cast<int>(t % halves); t /= halves;
+  int kc = static_cast<int>(t % im.kchunks); t /= im.kchunks;
+  const int g = static_cast<int>(t);
+  const int n = g * im.ng + hf * hrows + row;
+  bool lo_part = false;
+  if (im.split) {
+    lo_part = kc >= im.kchunks / 2;
+    kc %= im.kchunks / 2;
+  }
+  const int k = (kc * 2 * im.k16 + gr) * 8 + e;
+  const float* W = im.W;
+  float v = 0.f;
+  switch (im.kind) {
+    case PK_F0:
+      if (n < im.out_dim && k < 15) {
+        const float w = W[n * im.in_dim + (k % 3)];
+        const float hi = rnd16(w, dtype);
+        v = (k < 9) ? hi : rnd16(w - hi, dtype);
+      }
+      break;
+    case PK_FH:
+      if (n < im.out_dim && k < im.in_dim) v = im.scale * W[static_cast<long>(n) * im.in_dim + k];
+      break;
+    case PK_FL:
+      if (n == 0 && k < im.in_dim) v = W[k];
+      break;
+    case PK_RH:
+      if (k < im.out_dim && n < im.in_dim) v = im.scale * W[static_cast<long>(k) * im.in_dim + n];
+      break;
+    case PK_R0:
+      if (n < im.in_dim && k < im.out_dim) v = W[k * im.in_dim + n];
+      break;
+  }
+  if (lo_part) v = v - rnd16(v, dtype);
+  im.dst[idx] = bits16(v, dtype);
+}
+
+__global__ void pack_all_kernel(const __grid_constant__ PackAll pa) {
+  const long tid = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long nthr = static_cast<long>(gridDim.x) * blockDim.x;
+  for (int i = 0; i < pa.n_img; ++i) {
+    const PackImg& im = pa.img[i];
+    for (long idx = tid; idx < im.total; idx += nthr) pack_one(im, idx, pa.dtype, pa.halves);
+  }
+  if (pa.bias_dst) {
+    const long nb = static_cast<long>(pa.L + 1) * pa.H;
+    for (long idx = tid; idx < nb; idx += nthr) {
+      const int l = static_cast<int>(idx / pa.H), j = static_cast<int>(idx % pa.H);
+      pa.bias_dst[idx] = j < pa.b_out[l] ? pa.b[l][j] : 0.f;
+    }
+    for (long idx = tid; idx < pa.H; idx += nthr) pa.w_last_dst[idx] = pa.w_last_src[idx];
+  }
+}
+cudaError_t launch_pack_all(const PackAll& pa, cudaStream_t stream) {
+  pack_all_kernel<<<1184, 256, 0, stream>>>(pa);
+  return cudaGetLastError();
+}
+
+
+// Loss value from the (hi, lo) tail of the gradient buffer (after the cross-rank sum): out4 = {total, term0, term1, term2}.
+// kind 0: IGRLOSS (model/losses.py:118-136), kind 1: point-cloud loss (executor/executordistributed.py:73-79).
+__global__ void loss_value_kernel(const float* __restrict__ tail, int kind, float tau, float lambda_g, int data_term, double inv_n,
+                                  double inv_m, float* __restrict__ out4) {
+  double s[8];
+  for (int i = 0; i < 8; ++i) s[i] = static_cast<double>(tail[2 * i]) + static_cast<double>(tail[2 * i + 1]);
+  if (kind == 0) {
+    if (inv_n <= 0.0) inv_n = s[7] > 0.0 ? 1.0 / s[7] : 0.0;  // the count travels with the sums (global after the allreduce)
+    const double data = data_term == 0 ? s[1] * inv_n + s[3] * inv_n - 2.0 * (s[0] * inv_n) * (s[2] * inv_n) : s[4] * inv_n;
+    const double reg = s[5] * inv_n, eik = s[6] * inv_n;
+    out4[0] = static_cast<float>(data + tau * reg + lambda_g * eik);
+    out4[1] = static_cast<float>(data); out4[2] = static_cast<float>(reg); out4[3] = static_cast<float>(eik);
+  } else {
+    const double surf = s[0] * inv_n, eik = s[1] * inv_m;
+    out4[0] = static_cast<float>(surf + lambda_g * eik);
+    out4[1] = static_cast<float>(surf); out4[2] = static_cast<float>(eik); out4[3] = 0.f;
+  }
+}
+cudaError_t launch_loss_value(const float* tail, int kind, float tau, float lambda_g, int data_term, double inv_n, double inv_m,
+                              float* out4, cudaStream_t stream) {
+  loss_value_kernel<<<1, 1, 0, stream>>>(tail, kind, tau, lambda_g, data_term, inv_n, inv_m, out4);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Octree refinement flags, marching-cubes cell classification, ordered stream compaction.
-// Integer / predicate work: bit-exact against oracle/octree.py and oracle/marching.py given equal SDF inputs.
+// Integer / predicate work: bit-exact against oracle/sdf_oracle.py (octree_flags / octree_children / mc_cases) given equal SDF inputs.
 // ------------------------------------------------------------------------------------------------
 __global__ void octree_flags_kernel(const float* __restrict__ sdf, long n, float thresh, uint8_t* __restrict__ flags) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
@@ -630,6 +754,132 @@ cudaError_t launch_count_flags(const uint8_t* v, long n, int mode, long* total, 
   if (nb == 0) return cudaMemsetAsync(total, 0, sizeof(long), stream);
   compact_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(v, n, mode, scratch);
   compact_scan_kernel<<<1, kScanBlock, 0, stream>>>(scratch, nb, total);
+  return cudaGetLastError();
+}
+
+// ---- octree level loop without host round trips: the cell count of a level lives in DEVICE memory -------------------
+// lvl = {count, offset} of the level inside the key / sdf / flag arenas; the children of its flagged cells become the
+// next level, appended behind it: lvl_next = {8 * flagged, offset + count rounded up to even} (clamped to the arena capacity; *overflow = 1
+// then).  Same three ordered passes as launch_compact, each block looping over the tiles the device-side count yields.
+__global__ void octree_count_dev_kernel(const uint8_t* __restrict__ flags, const int64_t* __restrict__ lvl, long* __restrict__ block_counts) {
+  __shared__ int wsum[32];
+  const long n = lvl[0];
+  const uint8_t* v = flags + lvl[1];
+  const long ntiles = (n + kTileItems - 1) / kTileItems;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long base = tile * kTileItems;
+    int c = 0;
+    for (int t = 0; t < kItemsPerThread; ++t) {
+      const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+      if (i < n) c += v[i] != 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wsum[threadIdx.x];
+      for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+      if (threadIdx.x == 0) block_counts[tile] = w;
+    }
+    __syncthreads();
+  }
+}
+__global__ void octree_scan_dev_kernel(long* __restrict__ block_counts, const int64_t* __restrict__ lvl, int64_t* __restrict__ lvl_next,
+                                       long capacity, int* __restrict__ overflow) {
+  __shared__ long sh[kScanBlock];
+  __shared__ long carry;
+  const long n = lvl[0];
+  const long nblocks = (n + kTileItems - 1) / kTileItems;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long b0 = 0; b0 < nblocks; b0 += kScanBlock) {
+    const long i = b0 + threadIdx.x;
+    const long x = i < nblocks ? block_counts[i] : 0;
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+      long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nblocks) block_counts[i] = carry + sh[threadIdx.x] - x;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sh[kScanBlock - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const long off_next = (lvl[1] + n + 1) & ~1L;  // even: the 16-byte key stores of the scatter stay aligned
+    long children = 8 * carry;
+    if (off_next + children > capacity) {
+      children = off_next < capacity ? (capacity - off_next) / 8 * 8 : 0;
+      *overflow = 1;
+    }
+    lvl_next[0] = children;
+    lvl_next[1] = off_next;
+  }
+}
+__global__ void octree_scatter_dev_kernel(const uint8_t* __restrict__ flags, uint64_t* __restrict__ keys, const int64_t* __restrict__ lvl,
+                                          const int64_t* __restrict__ lvl_next, const long* __restrict__ block_offsets) {
+  __shared__ int wsum[32];
+  const long n = lvl[0];
+  const uint8_t* v = flags + lvl[1];
+  const uint64_t* kin = keys + lvl[1];
+  uint64_t* kout = keys + lvl_next[1];
+  const long max_cells = lvl_next[0] / 8;
+  const long ntiles = (n + kTileItems - 1) / kTileItems;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long base = tile * kTileItems;
+    int fl[kItemsPerThread];
+    int c = 0;
+    for (int t = 0; t < kItemsPerThread; ++t) {
+      const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+      fl[t] = i < n ? (v[i] != 0) : 0;
+      c += fl[t];
+    }
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wsum[lane];
+      int wi = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    long pos = block_offsets[tile] + wsum[warp] + (incl - c);
+    for (int t = 0; t < kItemsPerThread; ++t) {
+      if (fl[t]) {
+        if (pos < max_cells) {
+          const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+          const uint64_t k = kin[i];
+          // 8 consecutive child keys = 64 bytes: four 16-byte stores
+          ulonglong2* o2 = reinterpret_cast<ulonglong2*>(kout + pos * 8);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) o2[ch] = make_ulonglong2((k << 3) | static_cast<uint64_t>(2 * ch), (k << 3) | static_cast<uint64_t>(2 * ch + 1));
+        }
+        ++pos;
+      }
+    }
+    __syncthreads();
+  }
+}
+cudaError_t launch_octree_refine_dev(const uint8_t* flags, uint64_t* keys, const int64_t* lvl, int64_t* lvl_next, long* scratch,
+                                     long level_capacity, long capacity, int* overflow, cudaStream_t stream) {
+  long nb = compact_num_blocks(level_capacity);
+  if (nb < 1) nb = 1;
+  if (nb > 1184) nb = 1184;
+  octree_count_dev_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(flags, lvl, scratch);
+  octree_scan_dev_kernel<<<1, kScanBlock, 0, stream>>>(scratch, lvl, lvl_next, capacity, overflow);
+  octree_scatter_dev_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(flags, keys, lvl, lvl_next, scratch);
   return cudaGetLastError();
 }
 

@@ -951,7 +951,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   // ragged last pair works on the scratch tile n_tiles (all rows invalid, images inside the even-padded arrays)
   const int it0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int it_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int it_end = PAIR ? (p.n_tiles + 1) / 2 : p.n_tiles;
+  // device-side point count (octree level loop: the size of a level is the result of the previous level's compaction and
+  // never visits the host): lvl = {count, offset into keys / f_out / flag_out}; the grid was sized for p.n_tiles = capacity
+  const int64_t n_pts = p.lvl ? p.lvl[0] : p.n;
+  const int64_t lvl_off = p.lvl ? p.lvl[1] : 0;
+  const int n_tiles_rt = p.lvl ? static_cast<int>((n_pts + Cfg::kPoints - 1) / Cfg::kPoints) : p.n_tiles;
+  const int it_end = PAIR ? (n_tiles_rt + 1) / 2 : n_tiles_rt;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -1326,7 +1331,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
           (void)tile;
       e.grow = static_cast<int64_t>(tile) * PTS + e.prow;
-      e.valid = e.grow < p.n;
+      e.valid = e.grow < n_pts;
       // ---------------------------------------------------------------- prologue: input block (column groups 0, 1
       // write its two granules)
       const int first = p.steps[0].epi;
@@ -1351,7 +1356,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               e.x[2] = __ldg(p.axis + iz);
             } else {
               // octree cell centre from a 3-bit-per-level Morton key: c = -1 + (2 i + 1) * 2^-level
-              const uint64_t key = __ldg(p.keys + e.grow);
+              const uint64_t key = __ldg(p.keys + lvl_off + e.grow);
               uint32_t ci[3] = {0, 0, 0};
               for (int b = 0; b < p.level; ++b) {
                 ci[0] |= static_cast<uint32_t>((key >> (3 * b + 2)) & 1) << b;
@@ -1426,7 +1431,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                 const float z = v[0] + __ldg(p.bias + l * p.H);
                 // reference model/networks.py:104-105: tanh on the output when the activation is ReLU
                 e.fval = relu ? tanhf(z) : z;
-                if (e.valid && p.f_out) p.f_out[e.grow] = e.fval;
+                if (e.valid && p.f_out) p.f_out[lvl_off + e.grow] = e.fval;
+                // octree refinement predicate fused into the last forward epilogue (one fp32 compare, as
+                // oracle/sdf_oracle.py:octree_flags): |f| <= band * h_level, or every cell below the uniform level
+                if (e.valid && p.flag_out) p.flag_out[lvl_off + e.grow] = (p.flag_all || fabsf(e.fval) <= p.flag_thresh) ? 1 : 0;
               }
             }
           } break;
@@ -1565,13 +1573,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 template <int DT, bool PAR, bool PAIR, int SW = 3>
 static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device (per-context) function attribute: one flag per device
+  // ordinal, so a second device of the same process (nn.DataParallel, net.engine(device=1)) gets it too
+  static bool attr_set[kMaxDevices] = {};
   auto kfn = chain_kernel<DT, PAR, PAIR, SW>;
   constexpr uint32_t smem = ChainCfg<PAR, PAIR>::kSmem;
-  if (!attr_set) {
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];

@@ -146,12 +146,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
 }
 
 cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream) {
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[2][kMaxDevices] = {};  // per device: the shared-memory opt-in is a per-context attribute
   auto kfn = dtype == DT_BF16 ? dw_kernel<DT_BF16> : dw_kernel<DT_FP16>;
-  if (!attr_set[dtype]) {
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dtype][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDwSmem));
     if (e != cudaSuccess) return e;
-    attr_set[dtype] = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dtype][dev] = true;
   }
   if (n_items <= 0) return cudaSuccess;
   const int grid = n_items < num_sms ? n_items : num_sms;
@@ -386,12 +388,14 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity, int* __res
 
 cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, int* sync_ctr, int group,
                        cudaStream_t stream) {
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[2][kMaxDevices] = {};
   auto kfn = dtype == DT_BF16 ? dw2_kernel<DT_BF16> : dw2_kernel<DT_FP16>;
-  if (!attr_set[dtype]) {
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dtype][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDw2Smem));
     if (e != cudaSuccess) return e;
-    attr_set[dtype] = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dtype][dev] = true;
   }
   if (n_items <= 0) return cudaSuccess;
   int pairs = num_sms / 2;
@@ -413,7 +417,9 @@ cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int pari
     // The group barrier needs every CTA of the grid resident at once.  On an idle GPU that is what happens anyway (one
     // CTA per SM by shared memory); a cooperative launch makes it a guarantee when another stream's kernel holds SMs
     // (gang scheduling) instead of a possible deadlock.  If the launch is refused, run without the lock-step.
-    static bool coop_ok = true;
+    static bool coop_refused[kMaxDevices] = {};
+    bool& coop_ok_ref = coop_refused[dev >= 0 && dev < kMaxDevices ? dev : 0];
+    const bool coop_ok = !coop_ok_ref;
     if (coop_ok) {
       cudaLaunchConfig_t cfg = {};
       cudaLaunchAttribute attr[1];
@@ -428,7 +434,7 @@ cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int pari
       cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, items_dev, n_items, parity, sync_ctr, group, pairs_eff);
       if (e == cudaSuccess) return cudaGetLastError();
       cudaGetLastError();  // clear; fall back below
-      coop_ok = false;
+      coop_ok_ref = true;
     }
     group = 1;
     pairs_eff = pairs;

@@ -19,6 +19,7 @@ constexpr int kMaxH = 512;
 constexpr int kMaxLayers = 16;           // hidden layers
 constexpr int kMaxSteps = 2 * kMaxLayers + 4;
 constexpr int kStageBytes = 32768;       // one weight chunk (<= 256 rows x 64 K x 2 B)
+constexpr int kMaxDevices = 64;          // per-device launch state (function attributes) is kept per device ordinal
 constexpr int kXCols = 16;               // width of the input block (x / g-bar / f-bar split columns)
 
 // element type of the 16-bit operands
@@ -89,6 +90,10 @@ struct ChainParams {
   int64_t grid_off;        // flat index of the first point ((ix*n + iy)*n + iz ordering)
   const uint64_t* keys;    // SRC_OCTREE: Morton keys of the cells of one level
   int32_t level;
+  const int64_t* lvl;      // optional DEVICE {count, offset}: overrides n (and offsets keys / f_out / flag_out); n_tiles = capacity
+  uint8_t* flag_out;       // optional: octree refinement flags, written by the last forward epilogue
+  float flag_thresh;       // |f| <= flag_thresh  (band * h_level)
+  int32_t flag_all;        // 1: every cell is refined (levels below the uniform level)
   // outputs
   float* f_out;            // [n]
   float* g_out;            // [n][3]
@@ -130,6 +135,26 @@ struct DwItem {
   const uint8_t* X;                // nullptr: none
   uint32_t x_tstride;
   float* out_x;
+};
+
+// one launch packs every step image of a weight layout + biases + last-layer vector (aux.cu pack_all_kernel)
+struct PackImg {
+  const float* W;
+  uint16_t* dst;
+  int out_dim, in_dim, n_groups, ng, kchunks, k16, kind, split;
+  float scale;
+  long total;
+};
+constexpr int kMaxPackImgs = 2 * kMaxLayers + 2;
+struct PackAll {
+  PackImg img[kMaxPackImgs];
+  int n_img;
+  const float* b[kMaxLayers + 1];
+  int b_out[kMaxLayers + 1];
+  float* bias_dst;          // [(L+1)][H]; nullptr: weight images only
+  float* w_last_dst;        // [H]
+  const float* w_last_src;  // lin_L.weight
+  int H, L, dtype, halves;
 };
 
 __host__ __device__ inline uint32_t img_bytes(int H) { return static_cast<uint32_t>(H / 8) * kGranuleBytes; }

@@ -52,5 +52,11 @@ def subtree_owner(root_index, world=None):
 def broadcast_parameters(module, src=0):
     """Replicate the weights once (instead of DataParallel's broadcast per forward)."""
     if is_on() and dist.get_world_size() > 1:
-        for p in module.parameters():
-            dist.broadcast(p.data, src=src)
+        with torch.no_grad():
+            for p in module.parameters():
+                # p.detach() shares p's version counter (p.data does not): the in-place receive bumps it, so the engine's
+                # packed-weight cache sees the new values
+                dist.broadcast(p.detach(), src=src)
+    inner = module.module if hasattr(module, "module") else module
+    if hasattr(inner, "invalidate_packed"):
+        inner.invalidate_packed()

@@ -15,8 +15,24 @@ from . import _lib
 DTYPE_IDS = {"bf16": 0, "fp16": 1}
 PRECISION_IDS = {"fast": 0, "parity": 1}
 
-# default cap of the spill workspace of one training chunk (bytes); SDFNET_WS_GB overrides
-_WS_CAP_BYTES = int(float(os.environ.get("SDFNET_WS_GB", "64")) * (1 << 30))
+# cap of the spill workspace of one training chunk: SDFNET_WS_GB (GiB) if set, else 60 % of the device memory that is
+# free when the workspace is (re)allocated, at most 64 GiB -- larger batches are chunked by the library
+_WS_CAP_ENV = os.environ.get("SDFNET_WS_GB")
+_WS_CAP_MAX = 64 << 30
+
+
+def _ws_cap_bytes(device):
+    if _WS_CAP_ENV:
+        return int(float(_WS_CAP_ENV) * (1 << 30))
+    free, _total = torch.cuda.mem_get_info(device)
+    return max(min(int(0.6 * free), _WS_CAP_MAX), 1 << 26)
+
+
+class _RawCudaBuffer:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 def _ptr(t):
@@ -65,8 +81,16 @@ class Engine:
         self.handle = h
         self.num_params = int(self.lib.sdfnet_num_params(self.handle))
         self._ws = None
+        self._ws_capped = False
         self._packed_key = None
         self.launches = 0  # kernels launched through this engine (bench.py reports it as gpu_launches)
+        # fused step state: persistent loss-sum / label-stat / loss-value buffers, the gradient buffer view, and the
+        # hand-over of a finished backward to FusedAdam (optim.py)
+        self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self._stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._gbuf = None
+        self.acc_ready = False
+        self.pending_scale = None
 
     def __del__(self):
         try:
@@ -122,14 +146,21 @@ class Engine:
         self._packed_key = key
 
     # ------------------------------------------------------------------ scratch
+    def release_workspace(self):
+        """Give the spill workspace back to the caching allocator (e.g. before a large grid inference)."""
+        self._ws = None
+        self._ws_capped = False
+
     def workspace(self, n_points, mode):
         need = int(self.lib.sdfnet_workspace_bytes(self.handle, int(n_points), int(mode)))
-        need = min(need, _WS_CAP_BYTES)
-        per_tile = int(self.lib.sdfnet_workspace_bytes(self.handle, 256, int(mode)))  # 256 points = an even tile count
-        need = max(need, per_tile + 4096)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if self._ws is not None and (self._ws.numel() >= need or self._ws_capped):
+            return self._ws
+        held = 0 if self._ws is None else self._ws.numel()
+        self._ws = None  # returned to the caching allocator before the cap is computed from the free memory
+        floor = int(self.lib.sdfnet_workspace_bytes(self.handle, 256, int(mode))) + 4096  # 256 points = an even tile count
+        target = max(min(need, _ws_cap_bytes(self.device)), floor, held)
+        self._ws_capped = target < need  # the library chunks the batch; do not re-allocate on every call
+        self._ws = torch.empty(target, dtype=torch.uint8, device=self.device)
         return self._ws
 
     def _chunks(self, n, mode):
@@ -200,6 +231,50 @@ class Engine:
     def zero_grads(self):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sdfnet_zero_grads(self.handle, _stream(self.device)), "sdfnet_zero_grads")
+        self.acc_ready = False
+
+    def grad_buffer(self):
+        """Zero-copy fp32 view of [gradient accumulators | loss-sum tail] (library-owned): the one message a data-parallel
+        step all-reduces (include/sdfnet.h sdfnet_grad_buffer)."""
+        if self._gbuf is None:
+            ptr = ctypes.c_void_p()
+            n = ctypes.c_int64()
+            _lib.check(self.lib.sdfnet_grad_buffer(self.handle, ctypes.byref(ptr), ctypes.byref(n)), "sdfnet_grad_buffer")
+            self._gbuf = torch.as_tensor(_RawCudaBuffer(ptr.value, n.value), device=self.device)
+        return self._gbuf
+
+    def label_stats(self, y, delta):
+        """device double[2] = {sum clamp(y[:,0], +-delta), rows} of this shard (persistent buffer, overwritten per call)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_label_stats(_ptr(y), int(y.shape[0]), float(delta), _ptr(self._stats), _stream(self.device)),
+                       "sdfnet_label_stats")
+        self.launches += 1
+        return self._stats
+
+    def loss_value(self, kind, tau=0.0, lambda_g=0.0, data_term=0, n_global=0, m_global=0):
+        """float32[4] = {total, term0, term1, term2} from the (all-reduced) tail of the gradient buffer."""
+        out = torch.empty(4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_loss_value(self.handle, int(kind), float(tau), float(lambda_g), int(data_term), int(n_global),
+                                                  int(m_global), _ptr(out), _stream(self.device)), "sdfnet_loss_value")
+        self.launches += 1
+        return out
+
+    def fused_adam_step(self, weights, biases, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, grad_scale_dev=None,
+                        grads_out=None):
+        """Adam on the accumulated gradient + re-pack of the operand images, 2 kernels (include/sdfnet.h)."""
+        n = self.num_hidden + 1
+        wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in weights])
+        bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in biases])
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.sdfnet_fused_adam_step(self.handle, wp, bp, _ptr(exp_avg), _ptr(exp_avg_sq), float(lr), float(beta1), float(beta2),
+                                                float(eps), int(step), float(grad_scale), _ptr(grad_scale_dev), _ptr(grads_out),
+                                                _stream(self.device)),
+                "sdfnet_fused_adam_step",
+            )
+        self._pack_keep = list(weights) + list(biases)
+        self.launches += 2
 
     def read_grads(self, out=None, scale=1.0):
         if out is None:
@@ -248,6 +323,7 @@ class Engine:
                 "sdfnet_train_step_igr",
             )
         self.launches += 5 * self._chunks(n, 1)
+        self.acc_ready = False
 
     def train_step_pcd(self, x, n_global, xp, m_global, lambda_g, loss_sums):
         x = _check_points(x, 3, "surface points")

@@ -125,10 +125,9 @@ def octree_children(keys, flags):
 
 
 @torch.no_grad()
-def octree_build(model, max_level=10, refine_lvl_uni=3, band=SQRT3_2, rank=None, world=None):
-    """Adaptive octree of the zero level set down to ``max_level``.  Returns a list with one dict per level:
-    {level, keys, sdf, flags}.  With world > 1 each rank refines only the subtrees (cells of level
-    ``refine_lvl_uni``) dealt to it round-robin; there is no collective."""
+def octree_build_levelwise(model, max_level=10, refine_lvl_uni=3, band=SQRT3_2, rank=None, world=None):
+    """Host-driven level loop (one launch set and one host read of the child count per level).  Kept as the simple
+    form the device-side loop of ``octree_build`` is tested against."""
     from .losses import _unwrap
 
     net = _unwrap(model)
@@ -150,4 +149,67 @@ def octree_build(model, max_level=10, refine_lvl_uni=3, band=SQRT3_2, rank=None,
         keys = octree_children(keys, flags)
         if keys.numel() == 0:
             break
+    return levels
+
+
+def _even(v):
+    return (v + 1) & ~1
+
+
+@torch.no_grad()
+def octree_build(model, max_level=10, refine_lvl_uni=3, band=SQRT3_2, rank=None, world=None, capacity=None):
+    """Adaptive octree of the zero level set down to ``max_level``.  Returns a list with one dict per level:
+    {level, keys, sdf, flags} (views into three arenas).  The level loop runs on the DEVICE (``sdfnet_octree_levels``):
+    the cell count of a level is produced by the previous level's compaction and consumed by the next launch without
+    visiting the host; the refinement flags come out of the forward kernel's last epilogue.  One host read (the level
+    table) at the end.  With world > 1 each rank refines only the subtrees (cells of level ``refine_lvl_uni``) dealt to
+    it round-robin; there is no collective.  ``capacity``: total cells the arenas can hold (default 2^25)."""
+    from .losses import _unwrap
+
+    net = _unwrap(model)
+    eng = net.engine()
+    dev = eng.device
+    lib = _lib.load()
+    world = _dist.world_size() if world is None else world
+    rank = _dist.rank() if rank is None else rank
+    uni = min(int(refine_lvl_uni), int(max_level))
+    capacity = int(capacity) if capacity is not None else (1 << 25)
+    keys = torch.empty(capacity, dtype=torch.int64, device=dev)
+    sdf = torch.empty(capacity, dtype=torch.float32, device=dev)
+    flags = torch.empty(capacity, dtype=torch.uint8, device=dev)
+    # the uniform levels are known without evaluating anything: level l holds all 8^l Morton codes in order; the level the
+    # subtrees start at is dealt round-robin over the ranks
+    table = [[0, 0] for _ in range(max_level + 2)]
+    off = 0
+    for level in range(uni + 1):
+        if level == refine_lvl_uni and world > 1:
+            cnt = len(range(rank, 8 ** level, world))
+            if cnt:
+                keys[off:off + cnt] = torch.arange(rank, 8 ** level, world, dtype=torch.int64, device=dev)
+        else:
+            cnt = 8 ** level
+            keys[off:off + cnt] = torch.arange(cnt, dtype=torch.int64, device=dev)
+        if off + cnt > capacity:
+            raise RuntimeError(f"octree_build: capacity {capacity} too small for the uniform levels")
+        table[level] = [cnt, off]
+        off = _even(off + cnt)
+    table_dev = torch.tensor(table, dtype=torch.int64).to(dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.sdfnet_octree_levels(eng.handle, 0, int(max_level), int(refine_lvl_uni), float(band), _ptr(keys), _ptr(sdf), _ptr(flags),
+                                     capacity, _ptr(table_dev), _ptr(overflow), _stream(dev)),
+            "sdfnet_octree_levels",
+        )
+    eng.launches += (max_level + 1) + 3 * max(0, max_level - uni)
+    host = torch.cat([table_dev.view(-1), overflow.to(torch.int64)]).cpu()  # the one host read of the build
+    if int(host[-1]) != 0:
+        raise RuntimeError(f"octree_build: arena capacity {capacity} exceeded; pass a larger capacity=")
+    tbl = host[:-1].view(-1, 2).tolist()
+    levels = []
+    for level in range(max_level + 1):
+        cnt, o = tbl[level]
+        if cnt == 0 and level > 0:
+            break
+        levels.append({"level": level, "keys": keys[o:o + cnt], "sdf": sdf[o:o + cnt], "flags": flags[o:o + cnt]})
     return levels

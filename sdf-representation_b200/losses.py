@@ -33,19 +33,42 @@ def _unwrap(model):
 
 
 class _FusedLoss(torch.autograd.Function):
-    """loss value + precomputed flat parameter gradient -> a scalar whose backward scatters those gradients."""
+    """loss value -> a scalar whose backward hands the gradient the fused step has already accumulated to autograd.
+
+    The gradient lives in the engine's accumulators (summed over ranks).  If a ``FusedAdam`` (optim.py) drives the
+    network, backward only records d(total)/d(loss) as a device scalar and leaves the accumulators to the optimizer's
+    fused unpack + Adam + re-pack kernel (no per-tensor work at all, ``p.grad`` stays unset unless the optimizer was
+    built with ``materialize_grads=True``).  Otherwise the flat gradient is unpacked and scattered to ``p.grad`` so that
+    ``torch.optim.Adam`` (reference executor/executor.py:160,177) works unchanged."""
 
     @staticmethod
-    def forward(ctx, loss_value, flat_grads, *params):
-        ctx.save_for_backward(flat_grads)
+    def forward(ctx, loss_value, net, eng, *params):
+        ctx.net, ctx.eng = net, eng
         ctx.params = params
         return loss_value.clone()
 
     @staticmethod
     def backward(ctx, gout):
-        (flat,) = ctx.saved_tensors
+        eng = ctx.eng
+        opt = ctx.net._fused_optimizer()
+        if opt is not None and not opt.materialize_grads:
+            eng.pending_scale = gout.detach().to(torch.float32).reshape(1).contiguous()
+            eng.acc_ready = True
+            return (None, None, None, *([None] * len(ctx.params)))
+        flat = eng.read_grads()
         gp = [g * gout for g in _split_flat(flat, ctx.params)]
-        return (None, None, *gp)
+        if opt is not None:
+            eng.pending_scale = gout.detach().to(torch.float32).reshape(1).contiguous()
+            eng.acc_ready = True
+        return (None, None, None, *gp)
+
+
+def _global_counts(counts, device):
+    """Sum of per-rank row counts (host ints).  One small allreduce + host read; callers that know the global batch
+    pass it instead (``loss.global_rows``)."""
+    t = torch.tensor(list(counts), dtype=torch.int64, device=device)
+    _dist.all_reduce_sum(t)
+    return [int(v) for v in t.tolist()]
 
 
 def compute_normal(model, pj):
@@ -82,38 +105,31 @@ class IGRLOSS(nn.Module):
     def forward(self, x_batch, y_batch, model, epoch):
         net = _unwrap(model)
         eng = net._engine_for(x_batch)
-        dev = x_batch.device
-        n = x_batch.shape[0]
         world = _dist.world_size()
-        n_global = n * world
-        # global mean of the clamped labels (needed before the seeds exist in pairwise mode)
-        t_sum = y_batch[:, 0].detach().clamp(-self.delta, self.delta).sum(dtype=torch.float64).reshape(1)
-        _dist.all_reduce_sum(t_sum)
-        mean_t = (t_sum / n_global).to(torch.float32)
+        # {sum clamp(S), rows} of the whole batch, on the device: the pairwise data term needs the global label mean and
+        # every term the global normaliser BEFORE the seeds exist.  Rows travel with the label sum, so unequal shards
+        # (distributed.shard_rows with N % world != 0) use the right normaliser without any host value.
+        y_batch = y_batch.detach()
+        if y_batch.dtype != torch.float32 or not y_batch.is_contiguous():
+            y_batch = y_batch.float().contiguous()
+        stats = eng.label_stats(y_batch, self.delta)
+        if world > 1:
+            _dist.all_reduce_sum(stats)
         cfg = _lib.SdfnetIgrCfg(
             delta=float(self.delta), tau=float(self.tau), lambda_g=float(self.lambda_g),
             regularizer_threshold=float(self.regularizer_threshold),
-            data_term=0 if self.data_term == "pairwise" else 1, mean_t=0.0, n_global=int(n_global),
-            mean_t_dev=ctypes.c_void_p(mean_t.data_ptr()),
+            data_term=0 if self.data_term == "pairwise" else 1, mean_t=0.0, n_global=0,
+            mean_t_dev=ctypes.c_void_p(0), label_stats_dev=ctypes.c_void_p(stats.data_ptr()),
         )
-        sums = torch.zeros(8, dtype=torch.float64, device=dev)
         eng.zero_grads()
-        eng.train_step_igr(x_batch, y_batch, cfg, sums)
-        flat = eng.read_grads()
+        eng._sums.zero_()
+        eng.train_step_igr(x_batch, y_batch, cfg, eng._sums)
         if world > 1:
-            # one fp32 sum-allreduce of the whole gradient vector + one 8-double message with the loss sums
-            _dist.all_reduce_sum(flat)
-            _dist.all_reduce_sum(sums)
-        N = float(n_global)
-        if self.data_term == "pairwise":
-            data = sums[1] / N + sums[3] / N - 2.0 * (sums[0] / N) * (sums[2] / N)
-        else:
-            data = sums[4] / N
-        reg = sums[5] / N
-        eik = sums[6] / N
-        self.last_terms = torch.stack([data, reg, eik]).detach()
-        value = (data + self.tau * reg + self.lambda_g * eik).to(torch.float32)
-        return _FusedLoss.apply(value, flat, *net._ordered_params())
+            # ONE fp32 sum-allreduce: [gradient accumulators | loss sums] (replaces DataParallel's reduce into GPU 0)
+            _dist.all_reduce_sum(eng.grad_buffer())
+        out = eng.loss_value(0, tau=self.tau, lambda_g=self.lambda_g, data_term=0 if self.data_term == "pairwise" else 1)
+        self.last_terms = out[1:4]
+        return _FusedLoss.apply(out[0], net, eng, *net._ordered_params())
 
 
 class WeightedSmoothL2Loss(nn.Module):
@@ -167,6 +183,9 @@ class PointCloudLoss(nn.Module):
         super().__init__()
         self.lambda_g = lambda_g
         self.last_terms = None
+        # (rows of x, rows of x~) over all ranks if the caller knows them (it sharded the batch); None: summed over ranks
+        # with one small allreduce + host read per call
+        self.global_rows = None
 
     def __name__(self):
         return "PointCloudLoss"
@@ -176,15 +195,17 @@ class PointCloudLoss(nn.Module):
         eng = net._engine_for(x_batch)
         world = _dist.world_size()
         n, m = x_batch.shape[0], sampled_pts.shape[0]
-        sums = torch.zeros(8, dtype=torch.float64, device=x_batch.device)
+        if self.global_rows is not None:
+            n_global, m_global = (int(v) for v in self.global_rows)
+        elif world > 1:
+            n_global, m_global = _global_counts((n, m), x_batch.device)
+        else:
+            n_global, m_global = n, m
         eng.zero_grads()
-        eng.train_step_pcd(x_batch, n * world, sampled_pts, m * world, self.lambda_g, sums)
-        flat = eng.read_grads()
+        eng._sums.zero_()
+        eng.train_step_pcd(x_batch, n_global, sampled_pts, m_global, self.lambda_g, eng._sums)
         if world > 1:
-            _dist.all_reduce_sum(flat)
-            _dist.all_reduce_sum(sums)
-        surf = sums[0] / float(n * world)
-        eik = sums[1] / float(max(m * world, 1))
-        self.last_terms = torch.stack([surf, eik]).detach()
-        value = (surf + self.lambda_g * eik).to(torch.float32)
-        return _FusedLoss.apply(value, flat, *net._ordered_params())
+            _dist.all_reduce_sum(eng.grad_buffer())
+        out = eng.loss_value(1, lambda_g=self.lambda_g, n_global=n_global, m_global=max(m_global, 1))
+        self.last_terms = out[1:3]
+        return _FusedLoss.apply(out[0], net, eng, *net._ordered_params())

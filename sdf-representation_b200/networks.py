@@ -132,6 +132,8 @@ class ImplicitNet(nn.Module):
         # kernel-side description (validated when the first CUDA batch arrives)
         self._hidden = hidden
         object.__setattr__(self, "_engines", {})
+        object.__setattr__(self, "_fused_opt", None)  # weakref to the FusedAdam driving this network (optim.py)
+        object.__setattr__(self, "_pack_epoch", 0)    # bumped by invalidate_packed()
 
     def __name__(self):
         return "ImplicitNet"
@@ -140,7 +142,23 @@ class ImplicitNet(nn.Module):
         # engines hold raw library handles: never pickled / deep-copied, rebuilt lazily
         state = dict(self.__dict__)
         state["_engines"] = {}
+        state["_fused_opt"] = None
         return state
+
+    def _fused_optimizer(self):
+        ref = self.__dict__.get("_fused_opt")
+        return ref() if ref is not None else None
+
+    def invalidate_packed(self):
+        """Force a re-pack of the 16-bit operand images on the next launch.  The packed-weight cache is keyed on each
+        parameter's (data_ptr, version counter); writes that bypass the version counter (``p.data.copy_()``, a collective
+        on ``p.data``, a raw-pointer update from another library) must call this."""
+        object.__setattr__(self, "_pack_epoch", self.__dict__.get("_pack_epoch", 0) + 1)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+        return out
 
     # ------------------------------------------------------------------ engine plumbing
     def _ordered_params(self):
@@ -176,9 +194,12 @@ class ImplicitNet(nn.Module):
             H, L, skip = self._describe()
             eng = Engine(H, L, skip, float(self.beta) if self.beta > 0 else 0.0, x.device, dtype=self.dtype, precision=self.precision)
             self._engines[key] = eng
-        version = tuple((p.data_ptr(), p._version) for p in params)
-        eng.pack(params[0::2], params[1::2], key=version)
+        eng.pack(params[0::2], params[1::2], key=self._param_key(params))
         return eng
+
+    def _param_key(self, params=None):
+        params = self._ordered_params() if params is None else params
+        return (self.__dict__.get("_pack_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in params)
 
     def engine(self, device=None):
         """The engine bound to ``device`` (default: the parameters' device), with current weights packed."""

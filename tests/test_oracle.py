@@ -151,3 +151,99 @@ def test_adam_matches_torch():
         opt.step()
         p, m, v = orc.adam_step(p, g, m, v, 1e-3, step)
     assert torch.allclose(p, ref.detach(), atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ round 2 vectors
+def test_igr_mask_branch_matches_reference():
+    """regularizer_threshold (0.05) below delta (0.1): the where(|t| < thr, ., 1e-8) branch of model/losses.py:127-134."""
+    d = load_golden("round2_128x4.npz")
+    assert 0.05 < float(d["mask_frac"]) < 0.95  # both branches are exercised
+    W, b = golden_params(d)
+    x = torch.from_numpy(d["x"]).double()
+    y = torch.from_numpy(d["y"]).double()
+    loss, _, dW, db = orc.igr_loss_and_grads(W, b, x, y, skip_of(d), float(d["beta"]), 0.1, 1.0, 0.1, 0.05, "pairwise")
+    assert abs(float(loss) - float(d["mask_loss"])) < 2e-6 * max(1.0, abs(float(d["mask_loss"])))
+    gW, gb = golden_grads(d, "mask_grad_")
+    for l in range(len(W)):
+        assert rel_err(dW[l], gW[l]) < 2e-4, f"dW{l}"
+        assert rel_err(db[l], gb[l]) < 2e-4, f"db{l}"
+
+
+@pytest.mark.parametrize("tag,thr", [("pw", 1.0), ("pwmask", 0.05)])
+def test_igr_pointwise_matches_reference_arithmetic(tag, thr):
+    """data_term="pointwise": mean((p_i - t_i)^2) assembled from the reference's own forward / compute_normal
+    (oracle/make_golden.py ref_igr_pointwise)."""
+    d = load_golden("round2_128x4.npz")
+    W, b = golden_params(d)
+    x = torch.from_numpy(d["x"]).double()
+    y = torch.from_numpy(d["y"]).double()
+    loss, _, dW, db = orc.igr_loss_and_grads(W, b, x, y, skip_of(d), float(d["beta"]), 0.1, 1.0, 0.1, thr, "pointwise")
+    assert abs(float(loss) - float(d[tag + "_loss"])) < 2e-6 * max(1.0, abs(float(d[tag + "_loss"])))
+    gW, gb = golden_grads(d, tag + "_grad_")
+    for l in range(len(W)):
+        assert rel_err(dW[l], gW[l]) < 2e-4, f"dW{l}"
+        assert rel_err(db[l], gb[l]) < 2e-4, f"db{l}"
+
+
+def test_loss_curve_matches_reference_loop():
+    """60 steps of executor/executor.py:167-178 (IGRLOSS, Adam lr 4e-4) from identical weights and batches: the oracle's
+    sweeps + written-out Adam track the unmodified reference's loss curve and end at the same weights."""
+    d = load_golden("round2_128x4.npz")
+    L = int(d["num_hidden"])
+    W = [torch.from_numpy(d[f"curve_init_lin{i}_weight"]).double() for i in range(L + 1)]
+    b = [torch.from_numpy(d[f"curve_init_lin{i}_bias"]).double() for i in range(L + 1)]
+    px, py = torch.from_numpy(d["curve_x"]).double(), torch.from_numpy(d["curve_y"]).double()
+    mW = [torch.zeros_like(w) for w in W]; vW = [torch.zeros_like(w) for w in W]
+    mb = [torch.zeros_like(w) for w in b]; vb = [torch.zeros_like(w) for w in b]
+    curve = []
+    for i in range(60):
+        lo = 1024 * (i % 4)
+        loss, _, dW, db = orc.igr_loss_and_grads(W, b, px[lo:lo + 1024], py[lo:lo + 1024], skip_of(d), float(d["beta"]))
+        curve.append(float(loss))
+        for l in range(L + 1):
+            W[l], mW[l], vW[l] = orc.adam_step(W[l], dW[l], mW[l], vW[l], 4e-4, i + 1)
+            b[l], mb[l], vb[l] = orc.adam_step(b[l], db[l], mb[l], vb[l], 4e-4, i + 1)
+    ref = d["curve_loss"]
+    rel = np.abs(np.array(curve) / ref - 1).max()
+    assert ref[-1] < 0.7 * ref[0]  # the curve actually descends
+    # fp32 reference vs fp64 oracle through 60 Adam steps (Adam's g / sqrt(v) amplifies rounding of tiny gradients)
+    assert rel < 2e-3, rel
+    for l in range(L + 1):
+        assert rel_err(W[l], torch.from_numpy(d[f"curve_final_lin{l}_weight"])) < 2e-3
+
+
+def test_full_network_per_element_gradients_at_8192():
+    """BASELINE cfg 2 network at the reference's native batch scale (8192 points, [N,N] data term): every sampled
+    gradient element of all 18 tensors against the unmodified reference's autograd."""
+    d = load_golden("round2_full_8x512_n8192.npz")
+    shapes = orc.layer_shapes(3, [512] * 8, (4,))
+    import hashlib
+
+    torch.manual_seed(0)
+    W, b = [], []
+    for l, (o, i) in enumerate(shapes):  # replays model/networks.py:62-74 (nn.Linear default init, then geometric init)
+        lin = torch.nn.Linear(i, o)
+        if l == len(shapes) - 1:
+            torch.nn.init.normal_(lin.weight, mean=np.sqrt(np.pi) / np.sqrt(i), std=0.00001)
+            torch.nn.init.constant_(lin.bias, -1)
+        else:
+            torch.nn.init.constant_(lin.bias, 0.0)
+            torch.nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(o))
+        W.append(lin.weight.detach())
+        b.append(lin.bias.detach())
+    h = hashlib.sha256()
+    for w_, b_ in zip(W, b):
+        h.update(w_.numpy().tobytes())
+        h.update(b_.numpy().tobytes())
+    if h.hexdigest() != str(d["weights_sha256"]):
+        pytest.skip("torch build generates different seeded weights than the container that made the golden file")
+    x = torch.from_numpy(d["x"])
+    y = torch.from_numpy(d["y"])
+    loss, _, dW, db = orc.igr_loss_and_grads(W, b, x, y, (4,), 100.0)
+    assert abs(float(loss) - float(d["igr_loss"])) < 5e-6 * max(1.0, abs(float(d["igr_loss"])))
+    st = int(d["stride"])
+    for l in range(len(W)):
+        gw = dW[l].reshape(-1)[::st].numpy()
+        ew = np.abs(gw - d[f"igr_grad_lin{l}_weight"]).max() / float(d[f"igr_gmax_lin{l}_weight"])
+        eb = np.abs(db[l].numpy() - d[f"igr_grad_lin{l}_bias"]).max() / max(float(d[f"igr_gmax_lin{l}_bias"]), 1e-30)
+        assert ew < 1e-3 and eb < 1e-3, (l, ew, eb)  # fp32 vs fp32, different summation orders over 8192 points
