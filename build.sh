@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC -std=c++17"
 mkdir -p ../../build
 for f in chain dw aux api; do
-  if [ ! -f ../../build/$f.o ] || [ $f.cu -nt ../../build/$f.o ] || [ ptx.cuh -nt ../../build/$f.o ] || [ sdf_internal.h -nt ../../build/$f.o ] || [ ../../include/sdfnet.h -nt ../../build/$f.o ]; then
+  if [ ! -f ../../build/$f.o ] || [ $f.cu -nt ../../build/$f.o ] || [ mc_tables.h -nt ../../build/$f.o ] || [ ptx.cuh -nt ../../build/$f.o ] || [ sdf_internal.h -nt ../../build/$f.o ] || [ ../../include/sdfnet.h -nt ../../build/$f.o ]; then
     $NVCC $FLAGS -c $f.cu -o ../../build/$f.o &
   fi
 done

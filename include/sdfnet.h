@@ -166,6 +166,15 @@ int sdfnet_mc_compact(const uint8_t* case_index, int64_t n_cells, int64_t* activ
 int sdfnet_mc_edge_vertices(const float* sdf, int32_t nx, int32_t ny, int32_t nz, const int64_t* active_cells, int64_t n_active,
                             const float* spacing3, float* verts, uint16_t* edge_mask, void* stream);
 
+/* executor/executor.py:388 marching_cubes(...) -- the faces: for the active cells (ascending list of sdfnet_mc_compact) and
+ * their case indices, the triangles in cell order, each as three indices r * 12 + e into the [n_active][12] edge-vertex
+ * array of sdfnet_mc_edge_vertices (r = rank of the cell in active_cells, e = edge id), normals pointing from negative to
+ * positive sdf.  tri_vertex_index == NULL only counts the triangles into *n_tri (device) so the caller can size the
+ * buffer.  The triangle table is derived by a watertight-by-construction rule (tools/make_mc_table.py), not
+ * transcribed from skimage's Lewiner tables: same surface, same vertices, possibly different diagonals (parity unpinned). */
+int sdfnet_mc_triangles(const uint8_t* case_index, const int64_t* active_cells, int64_t n_active, int64_t* tri_vertex_index,
+                        int64_t* n_tri, void* stream);
+
 /* Instrumentation (no reference counterpart; used by bench.py): kernels launched through this handle so far, and
  * CUDA-event timing of each kernel class on its launch stream.  Classes: 0 = layer chain forward (+ reverse),
  * 1 = layer chain tangent + adjoint, 2 = weight-gradient GEMM, 3 = everything else.  sdfnet_profile_read waits for the

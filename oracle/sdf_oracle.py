@@ -13,6 +13,7 @@ The reference's own tests hold no golden vector for this path -
 marching-cubes cell classification have no reference counterpart at all and are "parity unpinned" (build-defined).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -297,6 +298,31 @@ def mc_edge_vertices(sdf, active, spacing=(1.0, 1.0, 1.0)):
         verts[:, e, :] = np.where(cross[:, None], v, np.float32(0))
         mask |= (cross.astype(np.uint16) << np.uint16(e)).astype(np.uint16)
     return verts, mask
+
+
+_MC_TABLE = None
+
+
+def mc_tri_table():
+    """(table [256, 15] uint8 edge ids padded with 255, count [256]) -- generated by tools/make_mc_table.py from a rule that
+    is watertight by construction (third-party skimage tables are not in /root/reference: parity unpinned)."""
+    global _MC_TABLE
+    if _MC_TABLE is None:
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "mc_tri_table.npz"))
+        _MC_TABLE = (d["table"], d["count"])
+    return _MC_TABLE
+
+
+def mc_triangles(cases, active):
+    """Faces of marching_cubes(sdf, 0.0) (executor/executor.py:388) for the active cells, in cell order then table order:
+    int64 [n_tri, 3] indices r * 12 + edge into the [n_active, 12] edge-vertex array of ``mc_edge_vertices``."""
+    table, count = mc_tri_table()
+    cs = np.asarray(cases).reshape(-1)[np.asarray(active, dtype=np.int64)]
+    out = []
+    for r, c in enumerate(cs):
+        for t in range(int(count[c])):
+            out.append([r * 12 + int(table[c, 3 * t + k]) for k in range(3)])
+    return np.asarray(out, dtype=np.int64).reshape(-1, 3)
 
 
 # ------------------------------------------------------------------------------------------------ octree

@@ -85,6 +85,7 @@ SIGNATURES = {
     "sdfnet_mc_classify": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sdfnet_mc_compact": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "sdfnet_mc_edge_vertices": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sdfnet_mc_triangles": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "sdfnet_octree_refine": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 

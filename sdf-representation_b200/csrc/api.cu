@@ -46,6 +46,7 @@ cudaError_t launch_mc_classify(const float* sdf, int nx, int ny, int nz, uint8_t
 cudaError_t launch_mc_edge_vertices(const float* sdf, int nx, int ny, int nz, const long* cells, long n_cells, float sx, float sy, float sz,
                                     float* verts, unsigned short* mask, cudaStream_t stream);
 long compact_num_blocks(long n);
+cudaError_t launch_mc_triangles(const uint8_t* cases, const long* cells, long n, long* tri, long* total, long* scratch, cudaStream_t stream);
 cudaError_t launch_octree_refine_dev(const uint8_t* flags, uint64_t* keys, const int64_t* lvl, int64_t* lvl_next, long* scratch,
                                      long level_capacity, long capacity, int* overflow, cudaStream_t stream);
 cudaError_t launch_count_flags(const uint8_t* v, long n, int mode, long* total, long* scratch, cudaStream_t stream);
@@ -442,13 +443,19 @@ static void prog_reverse(const sdfnet_handle* h, ChainParams& p, bool pr) {
   for (int l = h->L - 1; l >= 1; --l) add_step(p, EPI_REV_HIDDEN, l, &R[l]);
   add_step(p, EPI_REV_LAST, 0, &R[0]);
 }
+// SDFNET_NO_TAN_LAST=1 (measurement switch): separate last tangent layer and element-wise adjoint start, as in round 1
+static bool fuse_tan_last() {
+  static const bool on = [] { const char* e = getenv("SDFNET_NO_TAN_LAST"); return !(e && e[0] == '1'); }();
+  return on;
+}
 static void prog_tangent(const sdfnet_handle* h, ChainParams& p, bool pr) {
   const std::vector<StepImage>& F = pr ? h->Fp : h->F;
-  for (int l = 0; l < h->L; ++l) add_step(p, EPI_TAN_HIDDEN, l, &F[l]);
+  // the last tangent layer also forms Zbar_{L-1} (EPI_TAN_LAST): the adjoint sweep that follows starts at layer L-2
+  for (int l = 0; l < h->L; ++l) add_step(p, (l + 1 < h->L || !fuse_tan_last()) ? EPI_TAN_HIDDEN : EPI_TAN_LAST, l, &F[l]);
 }
-static void prog_adjoint(const sdfnet_handle* h, ChainParams& p, bool pr) {
+static void prog_adjoint(const sdfnet_handle* h, ChainParams& p, bool pr, bool after_tangent) {
   const std::vector<StepImage>& R = pr ? h->Rp : h->R;
-  add_step(p, EPI_ADJ_START, h->L - 1, nullptr);
+  if (!after_tangent || !fuse_tan_last()) add_step(p, EPI_ADJ_START, h->L - 1, nullptr);
   for (int l = h->L - 2; l >= 0; --l) add_step(p, EPI_ADJ_HIDDEN, l, &R[l + 1]);
 }
 
@@ -842,7 +849,7 @@ int run_ta(sdfnet_t h, int64_t m, const Spill& s, const float* fbar, const float
     p.flags |= FL_TANGENT;
     prog_tangent(h, p, h->pair_train);
   }
-  prog_adjoint(h, p, h->pair_train);
+  prog_adjoint(h, p, h->pair_train, gbar != nullptr);
   finish_program(p);
   Launch lr(h, PC_CHAIN_TA, stream);
   CU(launch_chain(p, h->d.dtype, h->parity ? 1 : 0, h->pair_train ? 1 : 0, h->num_sms, stream));
@@ -1082,6 +1089,20 @@ extern "C" int sdfnet_mc_edge_vertices(const float* sdf, int32_t nx, int32_t ny,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CU(launch_mc_edge_vertices(sdf, nx, ny, nz, reinterpret_cast<const long*>(active_cells), n_active, spacing3[0], spacing3[1], spacing3[2],
                              verts, edge_mask, stream));
+  return 0;
+}
+
+extern "C" int sdfnet_mc_triangles(const uint8_t* case_index, const int64_t* active_cells, int64_t n_active, int64_t* tri_vertex_index,
+                                   int64_t* n_tri, void* stream_) {
+  if (!case_index || !n_tri || (n_active > 0 && !active_cells)) return fail(1, "sdfnet_mc_triangles: null argument");
+  if (n_active < 0) return fail(1, "sdfnet_mc_triangles: negative cell count");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  long* scratch = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(long) * (compact_num_blocks(n_active) + 1), stream));
+  cudaError_t e = launch_mc_triangles(case_index, reinterpret_cast<const long*>(active_cells), n_active, reinterpret_cast<long*>(tri_vertex_index),
+                                      reinterpret_cast<long*>(n_tri), scratch, stream);
+  cudaFreeAsync(scratch, stream);
+  CU(e);
   return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 #include "sdf_internal.h"
+#include "mc_tables.h"
 
 namespace sdf {
 
@@ -880,6 +881,76 @@ cudaError_t launch_octree_refine_dev(const uint8_t* flags, uint64_t* keys, const
   octree_count_dev_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(flags, lvl, scratch);
   octree_scan_dev_kernel<<<1, kScanBlock, 0, stream>>>(scratch, lvl, lvl_next, capacity, overflow);
   octree_scatter_dev_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(flags, keys, lvl, lvl_next, scratch);
+  return cudaGetLastError();
+}
+
+// ---- marching-cubes faces: the triangles of the active cells, ordered (cell order, then table order) ------------------
+// Triangle t of active cell r (case index c) has the vertices r * 12 + kMcTriTable[c][3 t + k], k = 0..2 -- indices into
+// the [n_active][12] edge-vertex array of mc_edge_vertices_kernel.  Count pass per tile of cells, scan of the tile counts
+// (compact_scan_kernel), ordered write pass.  Table: mc_tables.h (generated, tools/make_mc_table.py).
+__global__ void mc_tri_count_kernel(const uint8_t* __restrict__ cases, const long* __restrict__ cells, long n, long* __restrict__ block_counts) {
+  __shared__ int wsum[32];
+  const long base = static_cast<long>(blockIdx.x) * kTileItems;
+  int c = 0;
+  for (int t = 0; t < kItemsPerThread; ++t) {
+    const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+    if (i < n) c += kMcTriCount[cases[cells[i]]];
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = wsum[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = w;
+  }
+}
+__global__ void mc_tri_write_kernel(const uint8_t* __restrict__ cases, const long* __restrict__ cells, long n,
+                                    const long* __restrict__ block_offsets, long* __restrict__ tri) {
+  __shared__ int wsum[32];
+  const long base = static_cast<long>(blockIdx.x) * kTileItems;
+  int cs[kItemsPerThread];
+  int c = 0;
+  for (int t = 0; t < kItemsPerThread; ++t) {
+    const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+    cs[t] = i < n ? cases[cells[i]] : 0;
+    c += kMcTriCount[cs[t]];
+  }
+  int incl = c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+    int wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    wsum[lane] = wi - w;
+  }
+  __syncthreads();
+  long pos = block_offsets[blockIdx.x] + wsum[warp] + (incl - c);
+  for (int t = 0; t < kItemsPerThread; ++t) {
+    const long i = base + static_cast<long>(threadIdx.x) * kItemsPerThread + t;
+    const int nt = kMcTriCount[cs[t]];
+    for (int q = 0; q < nt; ++q) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) tri[(pos + q) * 3 + k] = i * 12 + kMcTriTable[cs[t]][3 * q + k];
+    }
+    pos += nt;
+  }
+}
+cudaError_t launch_mc_triangles(const uint8_t* cases, const long* cells, long n, long* tri, long* total, long* scratch, cudaStream_t stream) {
+  const long nb = compact_num_blocks(n);
+  if (nb == 0) return cudaMemsetAsync(total, 0, sizeof(long), stream);
+  mc_tri_count_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(cases, cells, n, scratch);
+  compact_scan_kernel<<<1, kScanBlock, 0, stream>>>(scratch, nb, total);
+  if (tri) mc_tri_write_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, stream>>>(cases, cells, n, scratch, tri);
   return cudaGetLastError();
 }
 

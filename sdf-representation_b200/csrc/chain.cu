@@ -284,6 +284,11 @@ struct StepIO {
   uint8_t* out_u;       // tangent: u image
   const float* vec;     // forward: bias row
   bool special;         // the last three columns of this layer carry the raw input (skip injection)
+  // tangent / adjoint sweeps: the images the NEXT step of the program will read (just-in-time L2 prefetch, see
+  // hidden_step_staged_v1); cold: the previous step did not request this step's first pieces
+  const uint8_t* next_a;
+  const uint8_t* next_b;
+  bool cold;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -319,10 +324,37 @@ struct Piece {
   uint4 h[2];
   uint4 l[PAR ? 2 : 1];
 };
+// L2 eviction-priority hints (createpolicy encodings, as CUTLASS's TMA::CacheHintSm90): the spill images stream through
+// L2 exactly once per use -- 148 CTAs move ~76 MB per layer step, of the order of the L2 capacity -- so a line that has
+// been consumed (or written for a later kernel) should be the first victim, and a prefetched line should survive until
+// its one use.
+constexpr uint64_t kPolicyEvictFirst = 0x12F0000000000000ull;
+__device__ __forceinline__ uint4 ldg_v4_ef(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(kPolicyEvictFirst) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg_v4_ef(void* p, const uint4& v) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(kPolicyEvictFirst) : "memory");
+}
+#ifndef SDF_AUX_EF
+#define SDF_AUX_EF 0
+#endif
+#ifndef SDF_SPILL_EF
+#define SDF_SPILL_EF 0
+#endif
+// spill-image store of the tangent / adjoint sweeps
+__device__ __forceinline__ void stg_spill(uint8_t* p, const uint4& v) {
+  if (SDF_SPILL_EF) stg_v4_ef(p, v);
+  else *reinterpret_cast<uint4*>(p) = v;
+}
 template <bool PAR>
 __device__ __forceinline__ void ldg_piece(const Epi& e, int c, const uint8_t* img, Piece<PAR>& pk) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
+    if (SDF_AUX_EF && !PAR) { pk.h[j] = ldg_v4_ef(img + img_off(c + 8 * j, e.prow)); continue; }
     pk.h[j] = *reinterpret_cast<const uint4*>(img + img_off(c + 8 * j, e.prow));
     if (PAR) pk.l[j] = *reinterpret_cast<const uint4*>(img + img_off(c + 8 * j, e.prow + kParityPoints));
   }
@@ -433,6 +465,22 @@ __device__ __forceinline__ void granule_math(const Epi& e, const StepIO& io, con
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t] *= 1.f - a[t];
     if (last) { v[5] = e.x[0]; v[6] = e.x[1]; v[7] = e.x[2]; }  // tangent of the injected input = g-bar
+  } else if (EPI == EPI_TAN_LAST) {
+    // zdot_{L-1} in v.  adot = s' zdot -> AD spill (out_u);  Zbar_{L-1} = s' w_L fbar + beta (1 - s') q zdot -> result
+    float a[8];
+    granule8<DT, PAR>(xa, j, a);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a[t] = one_minus_dact(a[t], k);
+    float ad[8], q[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { ad[t] = v[t] * (1.f - a[t]); q[t] = 0.f; }
+    if (!k.relu) granule8<DT, PAR>(xb, j, q);
+    stg_granule8<DT, PAR>(e, io.out_u, c, ad);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(io.vec + c));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(io.vec + c + 4));
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = fmaf(k.beta * a[t] * q[t], v[t], (1.f - a[t]) * (w[t] * e.fb));
   } else if (EPI == EPI_ADJ_HIDDEN) {
     // Zbar_l = s' (Zbar_{l+1} W_{l+1}) + u_l
     float a[8];
@@ -544,7 +592,7 @@ __device__ __forceinline__ uint32_t word(const uint4& u, int i) { return i == 0 
 // bias row as fp32 bits).  Returns the packed result; *ou receives the packed u (tangent sweep).
 template <int DT, int EPI>
 __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& xa, const uint4& xb, const EpiConst& k,
-                                              uint32_t nbl2_2, bool has_b, uint4* ou) {
+                                              uint32_t nbl2_2, bool has_b, uint4* ou, const float* wl = nullptr) {
   uint32_t o[4];
   if (EPI == EPI_FWD_HIDDEN) {
     // a = max(z, 0) + log1p(exp(-beta |z|)) / beta.  The correction is at most ln2 / beta and the result is rounded to
@@ -573,12 +621,19 @@ __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& 
         const float w0 = v0 * ef.x, w1 = v1 * ef.y;             // (1 - s') zdot
         o[i] = H16<DT>::pack(v0 - w0, v1 - w1);                 // adot = s' zdot
         uo[i] = P2<DT>::mul(H16<DT>::pack(w0 * k.beta, w1 * k.beta), word(xb, i));  // u = beta (1 - s') zdot q
+      } else if (EPI == EPI_TAN_LAST) {
+        const float w0 = v0 * ef.x, w1 = v1 * ef.y;             // (1 - s') zdot
+        uo[i] = H16<DT>::pack(v0 - w0, v1 - w1);                // adot = s' zdot                    -> AD spill
+        const float2 qf = H16<DT>::unpack(word(xb, i));
+        // Zbar = s' (w_L fbar) + beta (1 - s') zdot q  (u stays in fp32 registers)           -> Z spill + next A operand
+        o[i] = H16<DT>::pack(fmaf(w0 * k.beta, qf.x, fmaf(-ef.x, wl[2 * i], wl[2 * i])),
+                             fmaf(w1 * k.beta, qf.y, fmaf(-ef.y, wl[2 * i + 1], wl[2 * i + 1])));
       } else {  // EPI_ADJ_HIDDEN
         o[i] = H16<DT>::pack(fmaf(-ef.x, v0, v0), fmaf(-ef.y, v1, v1));
         if (has_b) o[i] = P2<DT>::add(o[i], word(xb, i));       // + u
       }
     }
-    if (EPI == EPI_TAN_HIDDEN) *ou = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+    if (EPI == EPI_TAN_HIDDEN || EPI == EPI_TAN_LAST) *ou = make_uint4(uo[0], uo[1], uo[2], uo[3]);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -631,13 +686,44 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("pre
 // warps of an SM sub-partition cover each other's load latencies.
 // Overlapped hidden-layer epilogue, loop form: one piece at a time, both halves share the code.  Used by the tangent /
 // adjoint sweeps (the software-pipelined form below spills in their piece loop and measured 16 % slower there).
+// Just-in-time L2 prefetch of the tangent / adjoint sweeps (SDF_TA_PF_DIST = D > 0): while piece P is processed, the
+// lines of piece P + D are requested -- pieces of the NEXT step once P + D runs past this step's 8 pieces.  A line then
+// has to survive in L2 for D pieces (a few microseconds) instead of up to a whole layer step: with 148 CTAs streaming
+// ~76 MB per step through a 126 MB L2, the step-start burst (D = 0) loses its late lines again before they are used
+// (round 1: DRAM reads 16 % above the operand bytes, long-scoreboard stalls on the image loads).
+#ifndef SDF_TA_PF_DIST
+#define SDF_TA_PF_DIST 2
+#endif
+#ifndef SDF_PF_EL
+#define SDF_PF_EL 0
+#endif
+__device__ __forceinline__ void prefetch_l2_hint(const void* ptr) {
+  if (SDF_PF_EL) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ptr));
+  else asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+// first column of piece P (0..7) of a 512-wide step for this thread: half P / 4, chunk (P / 2) % 2, sub-piece P % 2
+__device__ __forceinline__ int piece_col(const Epi& e, int P) { return (P >> 2) * 256 + ((P >> 1) & 1) * 128 + e.h * 32 + (P & 1) * 16; }
+__device__ __forceinline__ void prefetch_piece(const Epi& e, const uint8_t* a, const uint8_t* b, int P) {
+  const int c = piece_col(e, P);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    prefetch_l2_hint(a + img_off(c + 8 * j, e.prow));
+    if (b) prefetch_l2_hint(b + img_off(c + 8 * j, e.prow));
+  }
+}
+
 template <int DT, int EPI>
 __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
-#ifndef SDF_NO_L2PF
+#if SDF_TA_PF_DIST > 0
+  if (io.cold) {
+#pragma unroll
+    for (int P = 0; P < SDF_TA_PF_DIST && P < 8; ++P) prefetch_piece(e, io.in_a, io.in_b, P);
+  }
+#elif !defined(SDF_NO_L2PF)
   // Every spill-image line the step will read is first requested into L2 (same-session A/B on B200: +3 % for the
   // tangent / adjoint sweeps, whose operands come from HBM; requesting the *next* step's lines instead: -18 %, L2 thrash)
-  if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) {
+  if (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN || EPI == EPI_TAN_LAST) {
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
@@ -694,6 +780,13 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
       const int c = c0 + (pc & 1) * 16;                        // first column of the piece
       uint32_t r[16];
       tmem_ld16(e.taddr + c, r);
+#if SDF_TA_PF_DIST > 0
+      {
+        const int T = half * 4 + pc + SDF_TA_PF_DIST;
+        if (T < 8) prefetch_piece(e, io.in_a, io.in_b, T);
+        else if (io.next_a) prefetch_piece(e, io.next_a, io.next_b, T - 8);
+      }
+#endif
 #ifdef SDF_CLOCKS
       if ((pc > 0 || half == 1) && !k.no_aux) load_aux<false, EPI>(e, io, c, xa, xb);
 #else
@@ -721,15 +814,23 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
           pq[j] = pack8<DT>(w);
         } else {
           uint4 ou;
-          pq[j] = granule_fast<DT, EPI>(w, xa.h[j], xb.h[j], k, nbl2_2, io.in_b != nullptr, &ou);
-          if (EPI == EPI_TAN_HIDDEN) *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
+          float wl[8];
+          if (EPI == EPI_TAN_LAST) {
+            // w_L[c..c+7] * fbar: the adjoint-start seed of this point (fp32 row of lin_L, L1-resident)
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(io.vec + c + 8 * j));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(io.vec + c + 8 * j + 4));
+            wl[0] = w0.x * e.fb; wl[1] = w0.y * e.fb; wl[2] = w0.z * e.fb; wl[3] = w0.w * e.fb;
+            wl[4] = w1.x * e.fb; wl[5] = w1.y * e.fb; wl[6] = w1.z * e.fb; wl[7] = w1.w * e.fb;
+          }
+          pq[j] = granule_fast<DT, EPI>(w, xa.h[j], xb.h[j], k, nbl2_2, io.in_b != nullptr, &ou, wl);
+          if (EPI == EPI_TAN_HIDDEN || EPI == EPI_TAN_LAST) stg_spill(io.out_u + img_off(c + 8 * j, e.prow), ou);
         }
       }
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
       const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       if (io.out) {
-        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = p0;
-        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = p1;
+        stg_spill(io.out + img_off(c, e.prow), p0);
+        stg_spill(io.out + img_off(c + 8, e.prow), p1);
       }
       if (half == 0) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
@@ -906,8 +1007,10 @@ __device__ __forceinline__ void hidden_step(Epi& e, const StepIO& io, const EpiC
 #ifndef SDF_TA_PIPE
 #define SDF_TA_PIPE 0
 #endif
-    if (!SDF_TA_PIPE && (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN)) hidden_step_staged_v1<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
-    else hidden_step_staged<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+    if constexpr (EPI == EPI_TAN_LAST || (!SDF_TA_PIPE && (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN)))
+      hidden_step_staged_v1<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+    else
+      hidden_step_staged<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
   }
   else hidden_step_plain<DT, PAR, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
   ++n0;
@@ -1413,6 +1516,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         io.out = io.out_u = nullptr;
         io.vec = nullptr;
         io.special = false;
+        io.next_a = io.next_b = nullptr;
+        io.cold = true;
+#if SDF_TA_PF_DIST > 0
+        if ((SW & 2) && (st.epi == EPI_TAN_HIDDEN || st.epi == EPI_ADJ_HIDDEN || st.epi == EPI_TAN_LAST)) {
+          // images the next step will read (just-in-time prefetch hands over from step to step)
+          if (s + 1 < p.n_steps) {
+            const StepDesc& nx = p.steps[s + 1];
+            if (nx.epi == EPI_TAN_HIDDEN || nx.epi == EPI_TAN_LAST) {
+              io.next_a = img_ptr(p.Aimg, nx.layer, p.tile_stride, tile, ib);
+              io.next_b = relu ? nullptr : img_ptr(p.Qimg, nx.layer, p.tile_stride, tile, ib);
+            } else if (nx.epi == EPI_ADJ_HIDDEN) {
+              io.next_a = img_ptr(p.Aimg, nx.layer, p.tile_stride, tile, ib);
+              io.next_b = has_u ? img_ptr(p.Uimg, nx.layer, p.tile_stride, tile, ib) : nullptr;
+            }
+          }
+          io.cold = !(s > 0 && (p.steps[s - 1].epi == EPI_TAN_HIDDEN || p.steps[s - 1].epi == EPI_ADJ_HIDDEN || p.steps[s - 1].epi == EPI_TAN_LAST));
+        }
+#endif
         switch (st.epi) {
           case EPI_FWD_HIDDEN: if (SW & 1) {
             io.out = ((p.flags & FL_SPILL_A) && !no_stg) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
@@ -1502,6 +1623,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             io.out_u = relu ? nullptr : img_ptr(p.Uimg, l, p.tile_stride, tile, ib);
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_TAN_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
+          } break;
+          case EPI_TAN_LAST: if (SW & 2) {
+            // last tangent layer + adjoint start in one epilogue: u_{L-1} is consumed where it is produced
+            io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
+            io.in_b = relu ? nullptr : img_ptr(p.Qimg, l, p.tile_stride, tile, ib);
+            io.out = no_stg ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
+            io.out_u = img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
+            io.vec = p.w_last;
+            hidden_step<DT, PAR, EPI_TAN_LAST>(e, io, k, st, B, n0, n1, gskip);
           } break;
           case EPI_ADJ_START: if (SW & 2) {
             // Zbar_{L-1} = s' * (w_L fbar) + u_{L-1}

@@ -35,6 +35,8 @@ enum : int {
   EPI_TAN_HIDDEN = 5,  // adot_l = act'(z_l) * zdot_l ; u_l = act''(z_l) s_l zdot_l   (spill AD, U)
   EPI_ADJ_START = 6,   // Zbar_{L-1} = act'(z_{L-1}) w_L fbar + u_{L-1}               (no GEMM)
   EPI_ADJ_HIDDEN = 7,  // Zbar_l = act'(z_l) (Zbar_{l+1} W_{l+1}) + u_l               (spill Z)
+  EPI_TAN_LAST = 8,    // last tangent layer fused with the adjoint start: adot_{L-1} (spill AD) and
+                       // Zbar_{L-1} = act'(z_{L-1}) w_L fbar + u_{L-1} -> next A operand (spill Z); u_{L-1} never leaves the SM
 };
 
 struct StepDesc {

@@ -110,6 +110,57 @@ def mc_edge_vertices(sdf_block, active, spacing=(1.0, 1.0, 1.0)):
     return verts, mask
 
 
+@torch.no_grad()
+def mc_triangles(cases, active):
+    """Faces of ``marching_cubes(sdf, level=0.0)`` (executor/executor.py:388) for the active cells: int64 [n_tri, 3], each
+    entry an index r * 12 + e into the flattened [n_active * 12, 3] vertex array of ``mc_edge_vertices`` (r = rank of the
+    cell in ``active``, e = edge id); normals point from negative to positive sdf.  Table: csrc/mc_tables.h."""
+    lib = _lib.load()
+    if not cases.is_cuda or cases.dtype != torch.uint8 or not active.is_cuda or active.dtype != torch.int64:
+        raise RuntimeError("mc_triangles needs the uint8 CUDA case volume and the int64 CUDA active-cell list of mc_classify")
+    cases = cases.contiguous()
+    active = active.contiguous()
+    dev = cases.device
+    n_tri = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfnet_mc_triangles(_ptr(cases), _ptr(active), active.numel(), _ptr(None), _ptr(n_tri), _stream(dev)),
+                   "sdfnet_mc_triangles")
+        tri = torch.empty((int(n_tri.item()), 3), dtype=torch.int64, device=dev)
+        if tri.numel():
+            _lib.check(lib.sdfnet_mc_triangles(_ptr(cases), _ptr(active), active.numel(), _ptr(tri), _ptr(n_tri), _stream(dev)),
+                       "sdfnet_mc_triangles")
+    return tri
+
+
+@torch.no_grad()
+def marching_cubes(sdf_block, spacing=(1.0, 1.0, 1.0), index_offset=(0, 0, 0)):
+    """Device-resident stand-in for ``skimage.measure.marching_cubes(sdf, level=0.0, spacing=spacing)`` at the reference
+    call site executor/executor.py:388: classification -> compaction -> edge vertices -> faces, the volume never leaves
+    HBM.  Returns (verts float32 [n_active * 12, 3], faces int64 [n_tri, 3]); vertices are per cell (not welded; STL, the
+    reference's export format, is a triangle soup anyway: ``verts[faces]``).  ``index_offset`` shifts the block's index
+    space (a slab [ix0, ix1) of a sharded grid passes (ix0, 0, 0)) before the spacing is applied."""
+    cases, active = mc_classify(sdf_block, compact=True)
+    verts, _mask = mc_edge_vertices(sdf_block, active, spacing)
+    faces = mc_triangles(cases, active)
+    verts = verts.view(-1, 3)
+    if any(index_offset):
+        off = torch.tensor([float(o) * float(s) for o, s in zip(index_offset, spacing)], dtype=torch.float32, device=verts.device)
+        # crossing vertices only: (0,0,0) rows of non-crossing edges are never referenced by a face
+        verts = verts + off
+    return verts, faces
+
+
+@torch.no_grad()
+def reconstruct_mesh(model, cubesize, halo=1):
+    """executor/executor.py:351-388 end to end on the device for THIS rank's slab of the grid (slab of the slowest axis
+    + ``halo`` plane so the cells between two slabs belong to exactly one rank): returns (verts, faces) in the
+    coordinates of marching_cubes(..., spacing=(2/n, 2/n, 2/n)) of the whole volume.  No collective."""
+    n = int(cubesize)
+    ix0, ix1, sdf = grid_sdf_sharded(model, n, halo=halo)
+    sp = (2.0 / n, 2.0 / n, 2.0 / n)
+    return marching_cubes(sdf, spacing=sp, index_offset=(ix0, 0, 0))
+
+
 # ---------------------------------------------------------------------------------------------- octree
 def octree_children(keys, flags):
     """Morton keys of the 8 children of every flagged cell, in order (device-side ordered compaction)."""

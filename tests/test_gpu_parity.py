@@ -474,7 +474,7 @@ def test_training_is_independent_of_workspace_chunking(monkeypatch):
     from sdf_representation_b200 import engine as eng_mod
 
     def run(cap_bytes):
-        monkeypatch.setattr(eng_mod, "_WS_CAP_BYTES", cap_bytes)
+        monkeypatch.setattr(eng_mod, "_ws_cap_bytes", lambda _dev: cap_bytes)
         torch.manual_seed(21)
         net = pkg.ImplicitNet(3, [256] * 3, (2,), 100.0, True, precision="fast").to(dev())
         g = torch.Generator().manual_seed(22)

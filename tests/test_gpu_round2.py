@@ -155,7 +155,7 @@ def test_loss_curve_matches_reference_loop(mode, optimizer):
         loss = crit(px[lo:lo + 1024], py[lo:lo + 1024], net, i)
         loss.backward()
         opt.step()
-        curve.append(loss)
+        curve.append(loss.detach())
     curve = torch.stack(curve).cpu().numpy()
     ref = d["curve_loss"]
     rel = np.abs(curve / ref - 1)
