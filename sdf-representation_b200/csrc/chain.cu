@@ -340,11 +340,22 @@ __device__ __forceinline__ void stg_v4_ef(void* p, const uint4& v) {
                ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(kPolicyEvictFirst) : "memory");
 }
 #ifndef SDF_AUX_EF
-#define SDF_AUX_EF 0
+#define SDF_AUX_EF 1
 #endif
 #ifndef SDF_SPILL_EF
-#define SDF_SPILL_EF 0
+#define SDF_SPILL_EF 1
 #endif
+#ifndef SDF_FR_SPILL_EF
+#define SDF_FR_SPILL_EF 0
+#endif
+#ifndef SDF_REV_PF_DIST
+#define SDF_REV_PF_DIST 0
+#endif
+// spill-image store of the forward / reverse sweeps (a, q images: read again only many layer steps later)
+__device__ __forceinline__ void stg_spill_fr(uint8_t* p, const uint4& v) {
+  if (SDF_FR_SPILL_EF) stg_v4_ef(p, v);
+  else *reinterpret_cast<uint4*>(p) = v;
+}
 // spill-image store of the tangent / adjoint sweeps
 __device__ __forceinline__ void stg_spill(uint8_t* p, const uint4& v) {
   if (SDF_SPILL_EF) stg_v4_ef(p, v);
@@ -940,6 +951,13 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       const int c = c0 + (pc & 1) * 16;                  // first column of the piece
       const int cn = pc < 3 ? half * 256 + ((pc + 1) >> 1) * 128 + cb + ((pc + 1) & 1) * 16 : 256 + cb;  // next piece
       if (!kTmemAhead) tmem_ld16(e.taddr + c, r[cur]);
+#if SDF_REV_PF_DIST > 0
+      if (EPI == EPI_REV_HIDDEN) {
+        const int T = half * 4 + pc + 1 + SDF_REV_PF_DIST;  // the operands of piece P + 1 are already being loaded
+        if (T < 8) prefetch_piece(e, io.in_a, nullptr, T);
+        else if (io.next_a) prefetch_piece(e, io.next_a, nullptr, T - 8);
+      }
+#endif
       if (!kAuxAhead && (pc > 0 || half == 1)) load_aux<false, EPI>(e, io, c, xa[ac], xb[ac]);
       tmem_ld_wait();
       if (kTmemAhead && pc < 3) tmem_ld16(e.taddr + cn, r[nxt]);
@@ -956,8 +974,8 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       }
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
       if (io.out) {
-        *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = pq[0];
-        *reinterpret_cast<uint4*>(io.out + img_off(c + 8, e.prow)) = pq[1];
+        stg_spill_fr(io.out + img_off(c, e.prow), pq[0]);
+        stg_spill_fr(io.out + img_off(c + 8, e.prow), pq[1]);
       }
       if (half == 0) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
@@ -1533,6 +1551,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           }
           io.cold = !(s > 0 && (p.steps[s - 1].epi == EPI_TAN_HIDDEN || p.steps[s - 1].epi == EPI_ADJ_HIDDEN || p.steps[s - 1].epi == EPI_TAN_LAST));
         }
+#endif
+#if SDF_REV_PF_DIST > 0
+        if ((SW & 1) && st.epi == EPI_REV_HIDDEN && s + 1 < p.n_steps && p.steps[s + 1].epi == EPI_REV_HIDDEN)
+          io.next_a = img_ptr(p.Aimg, p.steps[s + 1].layer - 1, p.tile_stride, tile, ib);
 #endif
         switch (st.epi) {
           case EPI_FWD_HIDDEN: if (SW & 1) {

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (one `ncu --set full` capture) into a small text file for profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_kernel.txt
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [top_n] [--json profiles/dram_bytes_per_point.json --points N] > profiles/rNN_kernel.txt
+
+``--json`` also writes the measured DRAM bytes per point of each kernel class (what bench.py reports as
+``roofline.traffic``), so that the number in the bench line is read from the committed capture, not typed in.
 
 Reads the report with `ncu -i ... --page raw --csv` and `--page source --csv` (no GPU needed).
 """
@@ -35,13 +38,36 @@ def ncu(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
+def kernel_class(name):
+    """bench.py's kernel classes from the (demangled) kernel name: chain_kernel<DT, PAR, PAIR, SW> with SW = 1 forward /
+    reverse programs, 2 tangent / adjoint programs."""
+    if "chain_kernel" in name:
+        args = name[name.index("<") + 1:name.index(">")].replace(" ", "").split(",") if "<" in name else []
+        sw = args[3] if len(args) > 3 else "3"
+        return "chain_tan_adj" if sw.startswith("2") else "chain_fwd_rev"
+    if "dw2_kernel" in name or "dw_kernel" in name:
+        return "dw_gemm"
+    return "other"
+
+
 def main():
-    rep = sys.argv[1]
-    top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    argv = [a for a in sys.argv[1:]]
+    json_out, points = None, None
+    if "--json" in argv:
+        i = argv.index("--json")
+        json_out = argv[i + 1]
+        del argv[i:i + 2]
+    if "--points" in argv:
+        i = argv.index("--points")
+        points = int(argv[i + 1])
+        del argv[i:i + 2]
+    rep = argv[0]
+    top_n = int(argv[1]) if len(argv) > 1 else 25
     rows = ncu(rep, "raw")
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     print(f"# {rep}")
+    traffic = {}
     for k, r in enumerate(rows[2:]):
         print(f"\n## launch {k}: {r[ix['Kernel Name']]}")
         for key in KEYS:
@@ -51,7 +77,18 @@ def main():
             def gb(key):
                 v, u = float(r[ix[key]]), units[ix[key]]
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
-            print(f"{'traffic (dram read + write) bytes':72s} {gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum'):.4g}")
+            tb = gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum')
+            print(f"{'traffic (dram read + write) bytes':72s} {tb:.4g}")
+            cls = kernel_class(r[ix['Kernel Name']])
+            traffic.setdefault(cls, []).append(tb)
+    if json_out and points:
+        import json
+        # one launch of each hot class per step at this size: the largest launch of the class is the step's kernel
+        out = {"source": f"ncu --set full capture {rep.split('/')[-1]} (tools/ncu_summary.py), bytes per point = dram read + write of the "
+                         f"class's launch / {points} points", "points": points,
+               "bytes_per_point": {c: max(v) / points for c, v in traffic.items() if c != "other"}}
+        with open(json_out, "w") as f:
+            json.dump(out, f, indent=1)
     src = ncu(rep, "source")
     blocks, hdr2, cur = [], None, None
     for r in src:
@@ -66,9 +103,16 @@ def main():
         return
     jx = {h: i for i, h in enumerate(hdr2)}
     stalls = [h for h in hdr2 if h.startswith("stall_") and "Not Issued" not in h]
+    # the source page holds one block per profiled launch IN THE ORDER OF THE RAW PAGE, each headed by its kernel name:
+    # label the tables with that name (round 1 numbered them and mis-assigned two) and drop byte-identical repeats
+    seen = set()
     for k, (name, b) in enumerate(blocks):
         samp = sum(int(r[jx["# Samples"]]) for r in b) or 1
-        print(f"\n## launch {k} warp-stall samples ({samp} total, {len(b)} SASS instructions)")
+        sig = (name, samp, len(b))
+        if sig in seen:
+            continue
+        seen.add(sig)
+        print(f"\n## warp-stall samples of {name} ({samp} total, {len(b)} SASS instructions)")
         tot = {s: sum(int(r[jx[s]]) for r in b) for s in stalls}
         for s, v in sorted(tot.items(), key=lambda t: -t[1])[:8]:
             print(f"  {s:28s} {100.0 * v / samp:5.1f} %")
