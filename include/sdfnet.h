@@ -132,6 +132,12 @@ int sdfnet_fused_adam_step(sdfnet_t h, float* const* weights, float* const* bias
                            float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* grad_scale_dev,
                            float* grads_out, void* stream);
 
+/* Reproducibility switch (the reference's cuBLAS SGEMM + ATen path gives the same bits on every run; the default
+ * split-K red.add of the weight-gradient GEMM does not).  on != 0: every split of a dW block stores into a private slot
+ * and a second pass adds the slots in split order; the loss sums go through per-block partials added in block order.
+ * Training results are then bit-identical from run to run on the same device and batch. */
+int sdfnet_set_deterministic(sdfnet_t h, int32_t on);
+
 /* model/losses.py:115 t = clamp(y[:,0], +-delta): out2 (device, double) = {sum t, n} of this shard's labels y [n,4].  Summed
  * over ranks it is the label_stats_dev of sdfnet_igr_cfg. */
 int sdfnet_label_stats(const float* y, int64_t n, float delta, double* out2, void* stream);

@@ -76,6 +76,7 @@ SIGNATURES = {
         [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int32,
          c_float, c_void_p, c_void_p, c_void_p],
     ),
+    "sdfnet_set_deterministic": (c_int32, [c_void_p, c_int32]),
     "sdfnet_label_stats": (c_int32, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "sdfnet_grad_buffer": (c_int32, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64)]),
     "sdfnet_loss_value": (c_int32, [c_void_p, c_int32, c_float, c_float, c_int32, c_int64, c_int64, c_void_p, c_void_p]),

@@ -18,10 +18,10 @@ cudaError_t launch_dw2(const DwItem* items_dev, int n_items, int dtype, int pari
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
                              float lambda_g, float thr, float mean_t, const float* mean_t_dev, const double* stats_dev, double inv_n,
                              int data_term, int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums,
-                             double* fbar_sum, cudaStream_t stream);
+                             double* fbar_sum, double* part, cudaStream_t stream);
 cudaError_t launch_label_stats(const float* y, int64_t n, float delta, double* out2, cudaStream_t stream);
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
-                             unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum, double* part,
                              cudaStream_t stream);
 cudaError_t launch_absmax(const float* v, int64_t n, unsigned* absmax, cudaStream_t stream);
 cudaError_t launch_seed_scale(unsigned* absmax, float* scale, const double* sums, const double* fbar_sum, float* tail,
@@ -33,7 +33,8 @@ cudaError_t launch_fused_adam(int H, int L, int skip, const float* main_acc, con
                               float scale, const float* scale_dev, float* grads_out, cudaStream_t stream);
 cudaError_t launch_loss_value(const float* tail, int kind, float tau, float lambda_g, int data_term, double inv_n, double inv_m,
                               float* out4, cudaStream_t stream);
-cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream);
+cudaError_t launch_sum(const float* v, int64_t n, double* out, double* part, cudaStream_t stream);
+cudaError_t launch_reduce_partials(float* acc, const float* partial, long n, int slots, cudaStream_t stream);
 cudaError_t launch_tanh_seeds(const float* f, const float* g, const float* fbar_in, const float* gbar_in, int64_t n,
                               float* fbar, float* gbar, cudaStream_t stream);
 cudaError_t launch_unpack_grads(int H, int L, int skip, const float* main_acc, const float* zx_acc, const float* qg_acc,
@@ -95,6 +96,7 @@ struct GradLayout {
 }  // namespace sdf
 
 constexpr size_t kGradTail = 32;
+constexpr size_t kDetBlocks = 4096;  // >= the grid of the seed kernels
 
 // cached work list of the weight-gradient kernels for one (workspace, tile count, order) combination
 struct DwPlan {
@@ -104,6 +106,9 @@ struct DwPlan {
   DwItem* items_dev = nullptr;
   DwItem* items_host = nullptr;   // pinned: the upload is a true async copy, no stream synchronisation
   int* sync = nullptr;
+  float* partial = nullptr;       // deterministic mode: [slots][acc_floats] private split-K outputs
+  int slots = 0;
+  int det = 0;
   uint64_t last_use = 0;
 };
 
@@ -142,6 +147,8 @@ struct sdfnet_handle {
   // epoch alternates with the full batches without any rebuild, synchronisation or pageable copy
   std::vector<DwPlan> plans;
   uint64_t plan_clock = 0;
+  bool deterministic = false;      // sdfnet_set_deterministic: fixed-order reductions everywhere (bit-identical reruns)
+  double* det_part = nullptr;      // per-block partial loss sums [kDetBlocks][16]
   long* oct_scratch = nullptr;     // block counts of the device-side octree compaction
   long oct_scratch_cap = 0;
   // instrumentation: kernels launched through this handle, and (when enabled) CUDA-event timing per kernel class
@@ -304,7 +311,9 @@ extern "C" int sdfnet_destroy(sdfnet_t h) {
   cudaFree(h->scale_dev);
   cudaFree(h->absmax_dev);
   cudaFree(h->oct_scratch);
+  cudaFree(h->det_part);
   for (auto& pl : h->plans) {
+    cudaFree(pl.partial);
     cudaFree(pl.items_dev);
     cudaFreeHost(pl.items_host);
     cudaFree(pl.sync);
@@ -671,15 +680,19 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
   const GradLayout& gl = h->gl;
   auto launch_plan = [&](DwPlan& pl) -> int {
     pl.last_use = ++h->plan_clock;
-    Launch lr(h, PC_DW, stream, pl.pair_n > 0 && pl.n > pl.pair_n ? 2 : 1);
+    if (pl.det) CU(cudaMemsetAsync(pl.partial, 0, sizeof(float) * pl.slots * h->acc_floats, stream));
+    Launch lr(h, PC_DW, stream, (pl.pair_n > 0 && pl.n > pl.pair_n ? 2 : 1) + (pl.det ? 1 : 0));
     if (pl.pair_n > 0)
       CU(launch_dw2(pl.items_dev, pl.pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, pl.sync, pl.group, stream));
     if (pl.n > pl.pair_n)
       CU(launch_dw(pl.items_dev + pl.pair_n, pl.n - pl.pair_n, h->d.dtype, h->parity ? 1 : 0, h->num_sms, stream));
+    if (pl.det) CU(launch_reduce_partials(h->acc, pl.partial, static_cast<long>(h->acc_floats), pl.slots, stream));
     return 0;
   };
+  const int det = h->deterministic ? 1 : 0;
   for (auto& pl : h->plans)
-    if (pl.ws == s.A && pl.tiles == tiles && pl.so == (second_order ? 1 : 0) && pl.n > 0) return launch_plan(pl);
+    if (pl.ws == s.A && pl.tiles == tiles && pl.so == (second_order ? 1 : 0) && pl.det == det && pl.n > 0) return launch_plan(pl);
+  int max_slots = 1;
   int dw_group = 1;
   std::vector<DwItem> items;
   const int nmb = H / 128 > 0 ? H / 128 : 1;
@@ -731,7 +744,7 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
             // what lets L2 serve their second reads -- but only the nh == 0 blocks add it to the result.
             d.X = s.X; d.x_tstride = xb;
             d.out_x = nh == 0 ? gl.zx_acc + static_cast<size_t>(l) * 16 * H + mb * 256 : nullptr;
-            items.push_back(d);
+            d.store = static_cast<uint32_t>(sp); items.push_back(d);
           }
     }
     pair_n = static_cast<int>(items.size());
@@ -757,7 +770,7 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
           d.b_off = static_cast<uint32_t>(nh) * (nb / 8) * kGranuleBytes;
           d.n = nb; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1;
           d.out = gl.main_acc + (static_cast<size_t>(l - 1) * H + static_cast<size_t>(nh) * nb) * H + mb * 128;
-          items.push_back(d);
+          d.store = static_cast<uint32_t>(sp); items.push_back(d);
         }
     }
     for (int mb = 0; mb < nmb; ++mb) {
@@ -768,27 +781,34 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
         d.A1 = s.Z + arr * l; d.B1 = s.X; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
         d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1;
         d.out = gl.zx_acc + static_cast<size_t>(l) * 16 * H + mb * 128;
-        items.push_back(d);
+        d.store = static_cast<uint32_t>(sp); items.push_back(d);
       }
       {  // a_{L-1}^T . Sblock -> dW_L term 1
         DwItem d{};
         d.A1 = s.A + arr * (L - 1); d.B1 = s.S; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
         d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1; d.out = gl.as_acc + mb * 128;
-        items.push_back(d);
+        d.store = static_cast<uint32_t>(sp); items.push_back(d);
       }
       if (second_order) {
         DwItem d{};  // q_0^T . Gblock -> dW_0 term 2
         d.A1 = s.Q; d.B1 = s.G; d.a_tstride = ib; d.b_tstride = xb; d.a_off = aoff; d.b_off = 0;
         d.n = 16; d.tile0 = t0; d.tile1 = t1; d.out_ld = H; d.inv_mult = h->scale_dev + 1; d.out = gl.qg_acc + mb * 128;
-        items.push_back(d);
+        d.store = static_cast<uint32_t>(sp); items.push_back(d);
         DwItem e{};  // adot_{L-1}^T . Xblock -> dW_L term 2 (col 15)
         e.A1 = s.AD + arr * (L - 1); e.B1 = s.X; e.a_tstride = ib; e.b_tstride = xb; e.a_off = aoff; e.b_off = 0;
         e.n = 16; e.tile0 = t0; e.tile1 = t1; e.out_ld = H; e.inv_mult = h->scale_dev + 1; e.out = gl.adx_acc + mb * 128;
-        items.push_back(e);
+        e.store = static_cast<uint32_t>(sp); items.push_back(e);
       }
     }
   }
   const int n_items = static_cast<int>(items.size());
+  if (det) {
+    // every item of split sp writes (plain stores) into slot sp: same offsets as in the accumulator
+    for (auto& d : items) {
+      const int sp = static_cast<int>(d.store);  // the builders below left the split index here
+      if (sp + 1 > max_slots) max_slots = sp + 1;
+    }
+  }
   // new plan: own device list, pinned host copy (true async upload, no synchronisation), own lock-step counters.  The
   // cache holds a few plans (full batch, ragged last batch, first / second order); the least recently used one is
   // recycled only after the stream has drained (a launch may still read it) -- not in steady state.
@@ -801,9 +821,22 @@ int run_dw(sdfnet_t h, const Spill& s, int tiles, bool second_order, cudaStream_
     pl = &h->plans[0];
     for (auto& q : h->plans) if (q.last_use < pl->last_use) pl = &q;
     CU(cudaStreamSynchronize(stream));
-    cudaFree(pl->items_dev); cudaFreeHost(pl->items_host); cudaFree(pl->sync);
+    cudaFree(pl->items_dev); cudaFreeHost(pl->items_host); cudaFree(pl->sync); cudaFree(pl->partial);
     *pl = DwPlan();
   }
+  if (det) {
+    CU(cudaMalloc(&pl->partial, sizeof(float) * max_slots * h->acc_floats));
+    for (auto& d : items) {
+      const size_t sp = d.store;
+      d.out = pl->partial + sp * h->acc_floats + (d.out - h->acc);
+      if (d.out_x) d.out_x = pl->partial + sp * h->acc_floats + (d.out_x - h->acc);
+      d.store = 1;
+    }
+    pl->slots = max_slots;
+  } else {
+    for (auto& d : items) d.store = 0;
+  }
+  pl->det = det;
   CU(cudaMalloc(&pl->items_dev, sizeof(DwItem) * n_items));
   CU(cudaMallocHost(&pl->items_host, sizeof(DwItem) * n_items));
   CU(cudaMalloc(&pl->sync, sizeof(int) * (pair_n + 64)));
@@ -902,7 +935,7 @@ extern "C" int sdfnet_backward(sdfnet_t h, const float* x, int64_t n, const floa
       fb = s.fbar;
       gb = gbar ? s.gbar : nullptr;
     }
-    if (fb) CU(launch_sum(fb, m, h->fbar_sum, stream));
+    if (fb) CU(launch_sum(fb, m, h->fbar_sum, h->deterministic ? h->det_part : nullptr, stream));
     {
       Launch ls(h, PC_OTHER, stream, 2 + (fb ? 1 : 0) + (gb ? 1 : 0));
       if (fb) CU(launch_absmax(fb, m, h->absmax_dev, stream));
@@ -935,7 +968,7 @@ extern "C" int sdfnet_train_step_igr(sdfnet_t h, const float* x, const float* y,
       CU(launch_igr_seeds(s.f, s.g, y + o * 4, m, cfg->delta, cfg->tau, cfg->lambda_g, cfg->regularizer_threshold,
                           cfg->mean_t, cfg->mean_t_dev, cfg->label_stats_dev, cfg->n_global > 0 ? 1.0 / static_cast<double>(cfg->n_global) : 0.0,
                           cfg->data_term, h->relu ? 1 : 0,
-                          h->absmax_dev, s.fbar, s.gbar, loss_sums, h->fbar_sum, stream));
+                          h->absmax_dev, s.fbar, s.gbar, loss_sums, h->fbar_sum, h->deterministic ? h->det_part : nullptr, stream));
       CU(launch_seed_scale(h->absmax_dev, h->scale_dev, loss_sums, h->fbar_sum, h->tail, stream));
     }
     if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
@@ -962,7 +995,7 @@ extern "C" int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int6
     {
       Launch ls(h, PC_OTHER, stream, 2);
       CU(launch_pcd_seeds(s.f, nullptr, m, 0, 1.f / static_cast<float>(n_global), h->relu ? 1 : 0, h->absmax_dev, s.fbar,
-                          nullptr, loss_sums, h->fbar_sum, stream));
+                          nullptr, loss_sums, h->fbar_sum, h->deterministic ? h->det_part : nullptr, stream));
       CU(launch_seed_scale(h->absmax_dev, h->scale_dev, loss_sums, h->fbar_sum, h->tail, stream));
     }
     if (int rc = run_ta(h, m, s, s.fbar, nullptr, stream)) return rc;
@@ -978,12 +1011,19 @@ extern "C" int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int6
     {
       Launch ls(h, PC_OTHER, stream, 2);
       CU(launch_pcd_seeds(s.f, s.g, m, 1, lambda_g / static_cast<float>(m_global), h->relu ? 1 : 0, h->absmax_dev, s.fbar,
-                          s.gbar, loss_sums, h->fbar_sum, stream));
+                          s.gbar, loss_sums, h->fbar_sum, h->deterministic ? h->det_part : nullptr, stream));
       CU(launch_seed_scale(h->absmax_dev, h->scale_dev, loss_sums, h->fbar_sum, h->tail, stream));
     }
     if (int rc = run_ta(h, m, s, s.fbar, s.gbar, stream)) return rc;
     if (int rc = run_dw(h, s, tiles, true, stream)) return rc;
   }
+  return 0;
+}
+
+extern "C" int sdfnet_set_deterministic(sdfnet_t h, int32_t on) {
+  if (!h) return fail(1, "sdfnet_set_deterministic: null handle");
+  if (on && !h->det_part) CU(cudaMalloc(&h->det_part, sizeof(double) * kDetBlocks * 16));
+  h->deterministic = on != 0;
   return 0;
 }
 

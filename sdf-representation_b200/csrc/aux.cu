@@ -42,25 +42,40 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// part == nullptr: one double atomicAdd per block and term (summation order = block completion order).
+// part != nullptr (deterministic mode): block b writes its partial sums to part[b * stride + off + i]; a single-warp kernel
+// adds them in block order afterwards (finalize_partials_kernel), so the result is bit-identical from run to run.
 template <int NS>
-__device__ __forceinline__ void block_accumulate(float (&v)[NS], double* sums) {
-  __shared__ float part[NS][32];
+__device__ __forceinline__ void block_accumulate(float (&v)[NS], double* sums, double* part = nullptr, int stride = 0, int off = 0) {
+  __shared__ float part_sh[NS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
     float w = warp_sum(v[i]);
-    if (lane == 0) part[i][warp] = w;
+    if (lane == 0) part_sh[i][warp] = w;
   }
   __syncthreads();
   if (warp == 0) {
     const int nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-      float w = lane < nw ? part[i][lane] : 0.f;
+      float w = lane < nw ? part_sh[i][lane] : 0.f;
       w = warp_sum(w);
-      if (lane == 0) atomicAdd(&sums[i], static_cast<double>(w));
+      if (lane == 0) {
+        if (part) part[static_cast<long>(blockIdx.x) * stride + off + i] = static_cast<double>(w);
+        else atomicAdd(&sums[i], static_cast<double>(w));
+      }
     }
   }
+}
+// *dst.p[i] += sum over blocks (in block order) of part[b * stride + i], i < stride
+struct PartDst { double* p[16]; };
+__global__ void finalize_partials_kernel2(const double* __restrict__ part, int nblocks, int stride, PartDst dst) {
+  const int i = threadIdx.x;
+  if (i >= stride || !dst.p[i]) return;
+  double acc = 0.0;
+  for (int b = 0; b < nblocks; ++b) acc += part[static_cast<long>(b) * stride + i];
+  *dst.p[i] += acc;
 }
 
 struct IgrCfgDev {
@@ -83,7 +98,7 @@ __device__ __forceinline__ void block_absmax(float m, unsigned* absmax) {
 //   L = D + tau mean(reg) + lambda mean(eik),  D = mean(p^2)+mean(t^2)-2 mean(p) mean(t)  |  mean((p-t)^2)
 __global__ void igr_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ y,
                                  long n, IgrCfgDev c, float* __restrict__ fbar, float* __restrict__ gbar,
-                                 double* __restrict__ sums, double* __restrict__ fbar_sum) {
+                                 double* __restrict__ sums, double* __restrict__ fbar_sum, double* __restrict__ part) {
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float fsum[1] = {0.f};
   float amax = 0.f;
@@ -137,16 +152,16 @@ __global__ void igr_seeds_kernel(const float* __restrict__ f, const float* __res
     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(fb), fabsf(bx)), fmaxf(fabsf(by), fabsf(bz))));
   }
   block_absmax(amax, c.absmax);
-  block_accumulate<8>(acc, sums);
+  block_accumulate<8>(acc, sums, part, 9, 0);
   __syncthreads();
-  block_accumulate<1>(fsum, fbar_sum);  // sum fbar = d L / d b_L
+  block_accumulate<1>(fsum, fbar_sum, part, 9, 8);  // sum fbar = d L / d b_L
 }
 
 // reference executor/executordistributed.py:73-79:  which = 0: surface points, L += mean |f|  (fbar = sign(f)/N);
 // which = 1: perturbed points, L += lambda mean (|g|-1)^2  (gbar = (lambda/M) 2 (|g|-1) g/|g|).  coef = 1/N or lambda/M.
 __global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __restrict__ g, long n, int which, float coef,
                                  int relu_tanh, unsigned* __restrict__ absmax, float* __restrict__ fbar, float* __restrict__ gbar,
-                                 double* __restrict__ sums, double* __restrict__ fbar_sum) {
+                                 double* __restrict__ sums, double* __restrict__ fbar_sum, double* __restrict__ part) {
   float acc[1] = {0.f};
   float fsum[1] = {0.f};
   float amax = 0.f;
@@ -175,15 +190,15 @@ __global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __res
     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(fb), fabsf(bx)), fmaxf(fabsf(by), fabsf(bz))));
   }
   block_absmax(amax, absmax);
-  block_accumulate<1>(acc, sums + which);
+  block_accumulate<1>(acc, sums + which, part, 2, 0);
   __syncthreads();
-  block_accumulate<1>(fsum, fbar_sum);
+  block_accumulate<1>(fsum, fbar_sum, part, 2, 1);
 }
 
-__global__ void sum_kernel(const float* __restrict__ v, long n, double* __restrict__ out) {
+__global__ void sum_kernel(const float* __restrict__ v, long n, double* __restrict__ out, double* __restrict__ part) {
   float acc[1] = {0.f};
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) acc[0] += v[i];
-  block_accumulate<1>(acc, out);
+  block_accumulate<1>(acc, out, part, 1, 0);
 }
 
 // {sum clamp(y[:,0], +-delta), count} of one shard's labels (y [n,4]; model/losses.py:115): what the pairwise data term and
@@ -207,14 +222,21 @@ static int seed_blocks(long n) {
 cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int64_t n, float delta, float tau,
                              float lambda_g, float thr, float mean_t, const float* mean_t_dev, const double* stats_dev, double inv_n,
                              int data_term, int relu_tanh, unsigned* absmax, float* fbar, float* gbar, double* sums,
-                             double* fbar_sum, cudaStream_t stream) {
+                             double* fbar_sum, double* part, cudaStream_t stream) {
   IgrCfgDev c;
   c.mean_t_dev = mean_t_dev;
   c.stats_dev = stats_dev;
   c.absmax = absmax;
   c.delta = delta; c.tau = tau; c.lambda_g = lambda_g; c.thr = thr; c.mean_t = mean_t;
   c.inv_n = static_cast<float>(inv_n); c.data_term = data_term; c.relu_tanh = relu_tanh;
-  igr_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, y, n, c, fbar, gbar, sums, fbar_sum);
+  const int nb = seed_blocks(n);
+  igr_seeds_kernel<<<nb, 256, 0, stream>>>(f, g, y, n, c, fbar, gbar, sums, fbar_sum, part);
+  if (part) {
+    PartDst d{};
+    for (int i = 0; i < 8; ++i) d.p[i] = sums + i;
+    d.p[8] = fbar_sum;
+    finalize_partials_kernel2<<<1, 32, 0, stream>>>(part, nb, 9, d);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_label_stats(const float* y, int64_t n, float delta, double* out2, cudaStream_t stream) {
@@ -222,9 +244,16 @@ cudaError_t launch_label_stats(const float* y, int64_t n, float delta, double* o
   return cudaGetLastError();
 }
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
-                             unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum,
+                             unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum, double* part,
                              cudaStream_t stream) {
-  pcd_seeds_kernel<<<seed_blocks(n), 256, 0, stream>>>(f, g, n, which, coef, relu_tanh, absmax, fbar, gbar, sums, fbar_sum);
+  const int nb = seed_blocks(n);
+  pcd_seeds_kernel<<<nb, 256, 0, stream>>>(f, g, n, which, coef, relu_tanh, absmax, fbar, gbar, sums, fbar_sum, part);
+  if (part) {
+    PartDst d{};
+    d.p[0] = sums + which;
+    d.p[1] = fbar_sum;
+    finalize_partials_kernel2<<<1, 32, 0, stream>>>(part, nb, 2, d);
+  }
   return cudaGetLastError();
 }
 // ReLU/tanh network: turn seeds w.r.t. (f = tanh z, g = (1-f^2) G) into seeds w.r.t. (z, G), see igr_seeds_kernel.
@@ -287,8 +316,14 @@ cudaError_t launch_seed_scale(unsigned* absmax, float* scale, const double* sums
   seed_scale_kernel<<<1, 1, 0, stream>>>(absmax, scale, sums, fbar_sum, tail);
   return cudaGetLastError();
 }
-cudaError_t launch_sum(const float* v, int64_t n, double* out, cudaStream_t stream) {
-  sum_kernel<<<seed_blocks(n), 256, 0, stream>>>(v, n, out);
+cudaError_t launch_sum(const float* v, int64_t n, double* out, double* part, cudaStream_t stream) {
+  const int nb = seed_blocks(n);
+  sum_kernel<<<nb, 256, 0, stream>>>(v, n, out, part);
+  if (part) {
+    PartDst d{};
+    d.p[0] = out;
+    finalize_partials_kernel2<<<1, 32, 0, stream>>>(part, nb, 1, d);
+  }
   return cudaGetLastError();
 }
 

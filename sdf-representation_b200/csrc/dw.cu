@@ -133,7 +133,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
           tmem_ld16(lane_addr + as * 256 + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(d.out + static_cast<size_t>(c0 + j) * d.out_ld + m, __uint_as_float(r[j]) * im);
+          for (int j = 0; j < 16; ++j) {
+            float* o = d.out + static_cast<size_t>(c0 + j) * d.out_ld + m;
+            if (d.store) *o = __uint_as_float(r[j]) * im;
+            else atomicAdd(o, __uint_as_float(r[j]) * im);
+          }
         }
       }
       tc_fence_before();
@@ -143,6 +147,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<512>(tmem_base);
+}
+
+// deterministic mode, second pass: acc[i] += partial[0][i] + partial[1][i] + ... in split order
+__global__ void reduce_partials_kernel(float* __restrict__ acc, const float* __restrict__ partial, long n, int slots) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < slots; ++k) s += partial[static_cast<long>(k) * n + i];
+    acc[i] += s;
+  }
+}
+cudaError_t launch_reduce_partials(float* acc, const float* partial, long n, int slots, cudaStream_t stream) {
+  reduce_partials_kernel<<<1184, 256, 0, stream>>>(acc, partial, n, slots);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_dw(const DwItem* items_dev, int n_items, int dtype, int parity, int num_sms, cudaStream_t stream) {
@@ -362,14 +379,22 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity, int* __res
           tmem_ld16(lane_addr + as * 256 + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(d.out + static_cast<size_t>(c0 + j) * d.out_ld + m, __uint_as_float(r[j]) * im);
+          for (int j = 0; j < 16; ++j) {
+            float* o = d.out + static_cast<size_t>(c0 + j) * d.out_ld + m;
+            if (d.store) *o = __uint_as_float(r[j]) * im;
+            else atomicAdd(o, __uint_as_float(r[j]) * im);
+          }
         }
         if (d.out_x) {
           uint32_t r[16];
           tmem_ld16(lane_addr + (as ^ 1) * 256, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(d.out_x + static_cast<size_t>(j) * d.out_ld + m, __uint_as_float(r[j]) * im);
+          for (int j = 0; j < 16; ++j) {
+            float* o = d.out_x + static_cast<size_t>(j) * d.out_ld + m;
+            if (d.store) *o = __uint_as_float(r[j]) * im;
+            else atomicAdd(o, __uint_as_float(r[j]) * im);
+          }
         }
       }
       tc_fence_before();

@@ -137,6 +137,9 @@ struct DwItem {
   const uint8_t* X;                // nullptr: none
   uint32_t x_tstride;
   float* out_x;
+  // 0: red.add into out (split-K partial sums meet in the accumulator in completion order); 1: plain store into a slot
+  // this item owns alone (deterministic mode: a second pass adds the slots in split order, api.cu)
+  uint32_t store;
 };
 
 // one launch packs every step image of a weight layout + biases + last-layer vector (aux.cu pack_all_kernel)

@@ -105,6 +105,7 @@ class ImplicitNet(nn.Module):
         *,
         precision=_DEFAULT_PRECISION,
         dtype=_DEFAULT_DTYPE,
+        deterministic=False,
     ):
         super().__init__()
         hidden = list(dims)
@@ -117,6 +118,7 @@ class ImplicitNet(nn.Module):
         self.beta = beta
         self.precision = precision
         self.dtype = dtype
+        self.deterministic = bool(deterministic)  # bit-identical gradients from run to run (Engine.set_deterministic)
         for layer in range(0, self.num_layers - 1):
             out_dim = dims[layer + 1] - d_in if layer + 1 in skip_in else dims[layer + 1]
             lin = nn.Linear(dims[layer], out_dim)
@@ -193,6 +195,8 @@ class ImplicitNet(nn.Module):
         if eng is None:
             H, L, skip = self._describe()
             eng = Engine(H, L, skip, float(self.beta) if self.beta > 0 else 0.0, x.device, dtype=self.dtype, precision=self.precision)
+            if getattr(self, "deterministic", False):
+                eng.set_deterministic(True)
             self._engines[key] = eng
         eng.pack(params[0::2], params[1::2], key=self._param_key(params))
         return eng

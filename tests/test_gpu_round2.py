@@ -291,6 +291,44 @@ def test_forward_repeats_are_bit_identical():
     assert int(bad) == 0
 
 
+def test_deterministic_mode_gives_bit_identical_gradients():
+    """deterministic=True: split-K partial sums of the weight-gradient GEMM land in private slots and are added in split
+    order, loss sums are added in block order -> loss and all 1.84 M gradients are the same BITS on every run (the
+    reference's SGEMM path is deterministic too); the default red.add path agrees to rounding."""
+    import sdf_representation_b200 as pkg
+
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand(150_001, 3, generator=g) * 2 - 1).to(dev())
+    y = orc.torus_labels(x.cpu()).float().to(dev())
+    crit = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)
+    runs = []
+    for det in (True, True, True, False):
+        torch.manual_seed(0)
+        net = pkg.ImplicitNet(3, [512] * 8, (4,), 100.0, True, precision="fast", deterministic=det).to(dev())
+        loss = crit(x, y, net, 0)
+        loss.backward()
+        runs.append((loss.detach().clone(), torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()))
+    for l, gflat in runs[1:3]:
+        assert torch.equal(l, runs[0][0]) and torch.equal(gflat, runs[0][1])
+    e = rel_err(runs[3][1].cpu(), runs[0][1].cpu())
+    print(f"deterministic vs red.add gradients: rel diff {e:.3e}")
+    assert e < 1e-5 and abs(float(runs[3][0]) - float(runs[0][0])) < 1e-6
+    # the point-cloud step and the generic first-order path as well
+    pcd = pkg.PointCloudLoss(0.1)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        net = pkg.ImplicitNet(3, [512] * 8, (4,), 100.0, True, precision="fast", deterministic=True).to(dev())
+        lp = pcd(x[:60_000], x[60_000:80_000], net, 0)
+        lp.backward()
+        g1 = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+        for p in net.parameters():
+            p.grad = None
+        pkg.WeightedSmoothL2Loss(0.5, 0.1)(x[:30_000], y[:30_000], net, 0).backward()
+        outs.append((lp.detach().clone(), g1, torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()))
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
 # ------------------------------------------------------------------------------------------------ octree
 def test_octree_device_loop_bit_exact_to_level_10():
     """BASELINE configs[4]: the device-side level loop (counts never leave the GPU, flags from the forward epilogue)
