@@ -387,13 +387,17 @@ def main():
 
         # ---- (c) BASELINE configs[3]: dense grid, slab of the slowest axis per rank + 1 halo plane, marching-cubes cell
         # classification + compaction on the slab (executor/executor.py:351-388), no collective
+        # (grid and octree run on the seed-0 geometric-init network, f ~ |x| - 1: the same surface at every N, so the
+        # 1/2/4/8-GPU figures are comparable -- the trained weights above depend on the global batch)
+        torch.manual_seed(0)
+        inet = pkg.ImplicitNet(3, [512] * 8, (4,), 100.0, True, precision=args.precision, dtype=args.dtype).to(dev)
         gn = args.grid_n
         reps = 3
         ix0, ix1 = pkg.distributed.slab_bounds(gn, rank, world)
         hi = min(gn, ix1 + 1)
         slab = torch.empty((hi - ix0) * gn * gn, dtype=torch.float32, device=dev)
-        inference.grid_sdf(net, gn, ix0, min(ix0 + 2, hi))  # warm-up (packs the inference weight layout)
-        ms_grid = timed(lambda i: inference.grid_sdf(net, gn, ix0, hi, out=slab), reps) / reps
+        inference.grid_sdf(inet, gn, ix0, min(ix0 + 2, hi))  # warm-up (packs the inference weight layout)
+        ms_grid = timed(lambda i: inference.grid_sdf(inet, gn, ix0, hi, out=slab), reps) / reps
         block = slab.view(hi - ix0, gn, gn)
         n_act = []
 
@@ -408,14 +412,14 @@ def main():
             "n": gn, "planes_per_rank": ix1 - ix0, "halo": hi - ix1, "repeats": reps, "ms_grid_eval": ms_grid, "ms_mc_classify_compact": ms_mc,
             "queries_per_s": gn ** 3 / (ms_grid * 1e-3), "queries_per_s_incl_mc": gn ** 3 / ((ms_grid + ms_mc) * 1e-3),
             "frac_of_tensor_peak": (q_own + (hi - ix1) * gn * gn) * F_FLOP / (ms_grid * 1e-3) / 1e12 / peak_tf,
-            "active_cells_rank0": n_act[-1],
+            "active_cells_rank0": n_act[-1], "weights": "seed-0 geometric init (sphere of radius ~1)",
             "note": "whole-job queries/s = n^3 / max-over-ranks time; every rank evaluates its slab + 1 halo plane and classifies its own cells",
         }
         del slab, block
 
         # ---- (d) BASELINE configs[4]: adaptive octree to level 10, device-side level loop, subtrees sharded over ranks
         def oct_build(i):
-            return inference.octree_build(net, max_level=10, refine_lvl_uni=3, rank=rank, world=world)
+            return inference.octree_build(inet, max_level=10, refine_lvl_uni=3, rank=rank, world=world)
 
         lv = oct_build(0)
         reps_o = 3

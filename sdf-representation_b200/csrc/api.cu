@@ -441,14 +441,22 @@ static void base_params(const sdfnet_handle* h, ChainParams& p) {
   p.flags |= dbg & 0xffff0000u;
 }
 // pr: build the program on the CTA-pair weight layout (the launch must then use the pair kernel)
+// Fast mode at width 512 (the overlapped epilogue): the last hidden layer's epilogue also forms the network output by an
+// in-register dot product and, when a reverse sweep follows, its first operand -- no N = 16 output GEMM step and no
+// element-wise reverse-start step (EPI_FWD_FUSED).  SDFNET_NO_FWD_FUSED=1 keeps the separate steps (measurement switch).
+static bool fuse_fwd_last(const sdfnet_handle* h) {
+  static const bool on = [] { const char* e = getenv("SDFNET_NO_FWD_FUSED"); return !(e && e[0] == '1'); }();
+  return on && !h->parity && !h->relu && h->H == 512;
+}
 static void prog_forward(const sdfnet_handle* h, ChainParams& p, bool pr) {
   const std::vector<StepImage>& F = pr ? h->Fp : h->F;
-  for (int l = 0; l < h->L; ++l) add_step(p, EPI_FWD_HIDDEN, l, &F[l]);
-  add_step(p, EPI_FWD_LAST, h->L, &F[h->L]);
+  const bool fused = fuse_fwd_last(h);
+  for (int l = 0; l < h->L; ++l) add_step(p, (fused && l + 1 == h->L) ? EPI_FWD_FUSED : EPI_FWD_HIDDEN, l, &F[l]);
+  if (!fused) add_step(p, EPI_FWD_LAST, h->L, &F[h->L]);
 }
 static void prog_reverse(const sdfnet_handle* h, ChainParams& p, bool pr) {
   const std::vector<StepImage>& R = pr ? h->Rp : h->R;
-  add_step(p, EPI_REV_START, h->L - 1, nullptr);
+  if (!fuse_fwd_last(h)) add_step(p, EPI_REV_START, h->L - 1, nullptr);
   for (int l = h->L - 1; l >= 1; --l) add_step(p, EPI_REV_HIDDEN, l, &R[l]);
   add_step(p, EPI_REV_LAST, 0, &R[0]);
 }

@@ -289,6 +289,7 @@ struct StepIO {
   const uint8_t* next_a;
   const uint8_t* next_b;
   bool cold;
+  const float* wl;      // EPI_FWD_FUSED: fp32 row of the output layer lin_L
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -420,7 +421,7 @@ __device__ __forceinline__ void put_granule8(const Epi& e, uint8_t* img, int c, 
 // other sweeps = the activation image (xa) and the q / u image (xb).
 template <bool PAR, int EPI>
 __device__ __forceinline__ void load_aux(const Epi& e, const StepIO& io, int c, Piece<PAR>& xa, Piece<PAR>& xb) {
-  if (EPI == EPI_FWD_HIDDEN) {
+  if (EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_FUSED) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       xa.h[j] = __ldg(reinterpret_cast<const uint4*>(io.vec + c + 8 * j));
@@ -603,9 +604,36 @@ __device__ __forceinline__ uint32_t word(const uint4& u, int i) { return i == 0 
 // bias row as fp32 bits).  Returns the packed result; *ou receives the packed u (tangent sweep).
 template <int DT, int EPI>
 __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& xa, const uint4& xb, const EpiConst& k,
-                                              uint32_t nbl2_2, bool has_b, uint4* ou, const float* wl = nullptr) {
+                                              uint32_t nbl2_2, bool has_b, uint4* ou, const float* wl = nullptr, float* dot = nullptr) {
   uint32_t o[4];
-  if (EPI == EPI_FWD_HIDDEN) {
+  if (EPI == EPI_FWD_FUSED) {
+    // a = softplus(z + b) as in EPI_FWD_HIDDEN (-> *ou, the A spill); f accumulates w_L . a in fp32; has_b: a reverse sweep
+    // follows and the result is q = w_L * act'(z) = w_L (1 - exp(-beta a)) (model/losses.py:289-295 seeds grad_outputs = 1)
+    const float b[8] = {__uint_as_float(xa.x), __uint_as_float(xa.y), __uint_as_float(xa.z), __uint_as_float(xa.w),
+                        __uint_as_float(xb.x), __uint_as_float(xb.y), __uint_as_float(xb.z), __uint_as_float(xb.w)};
+    uint32_t ao[4];
+    float d = *dot;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t zh = H16<DT>::pack(v[2 * i] + b[2 * i], v[2 * i + 1] + b[2 * i + 1]);
+      const uint32_t ex = P2<DT>::ex2(P2<DT>::mul(P2<DT>::abs(zh), nbl2_2));
+      uint32_t pl = P2<DT>::fma(ex, k.sp2[3], k.sp2[2]);
+      pl = P2<DT>::fma(pl, ex, k.sp2[1]);
+      pl = P2<DT>::fma(pl, ex, k.sp2[0]);
+      ao[i] = P2<DT>::fma(pl, ex, P2<DT>::max(zh, 0u));
+      const float2 af = H16<DT>::unpack(ao[i]);
+      d = fmaf(af.x, wl[2 * i], d);
+      d = fmaf(af.y, wl[2 * i + 1], d);
+      if (has_b) {
+        const float2 ef = H16<DT>::unpack(P2<DT>::ex2(P2<DT>::mul(ao[i], nbl2_2)));  // exp(-beta a) = 1 - act'(z)
+        o[i] = H16<DT>::pack(fmaf(-ef.x, wl[2 * i], wl[2 * i]), fmaf(-ef.y, wl[2 * i + 1], wl[2 * i + 1]));
+      } else {
+        o[i] = ao[i];
+      }
+    }
+    *dot = d;
+    *ou = make_uint4(ao[0], ao[1], ao[2], ao[3]);
+  } else if (EPI == EPI_FWD_HIDDEN) {
     // a = max(z, 0) + log1p(exp(-beta |z|)) / beta.  The correction is at most ln2 / beta and the result is rounded to
     // 16 bits anyway, so it is evaluated on packed pairs: one MUFU (ex2) per element instead of ex2 + lg2 - the
     // forward epilogue was MUFU-bound (ncu: mio-throttle stalls on every MUFU) - and a cubic on the FMA pipe.
@@ -878,12 +906,17 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
 template <int DT, int EPI>
 __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                                    uint32_t par0, uint32_t par1, float* gskip) {
-  constexpr bool kFwd = EPI == EPI_FWD_HIDDEN;
+  constexpr bool kFwd = EPI == EPI_FWD_HIDDEN || EPI == EPI_FWD_FUSED;
+  constexpr bool kFused = EPI == EPI_FWD_FUSED;
+  // kFused, forward-only program (st.signal == 0): nothing reads the A image after this step -- the epilogue only
+  // accumulates the output dot product (no parking, no shared-memory stores)
+  const bool keep = !kFused || st.signal != 0;
+  float dot = 0.f;
   // Software pipeline of a warp (ncu: the sweeps that read spill images sat on the scoreboard of those loads, 60 % of
   // the reverse epilogue's samples): the accumulator piece p + 1 is read from TMEM and the spill-image operands of
   // piece p + 1 are requested while piece p is being processed.  The forward sweep's only memory operand is the bias
   // row (L1-resident), loaded per piece.
-  constexpr int kSweepBit = EPI == EPI_FWD_HIDDEN ? 1 : EPI == EPI_REV_HIDDEN ? 2 : EPI == EPI_TAN_HIDDEN ? 4 : 8;
+  constexpr int kSweepBit = kFwd ? 1 : EPI == EPI_REV_HIDDEN ? 2 : EPI == EPI_TAN_HIDDEN ? 4 : 8;
   constexpr bool kTmemAhead = (SDF_TMEM_AHEAD & kSweepBit) != 0;
   constexpr bool kAuxAhead = !kFwd && (SDF_AUX_AHEAD & kSweepBit) != 0;
   constexpr int kUnrollHalves = (EPI == EPI_TAN_HIDDEN || EPI == EPI_ADJ_HIDDEN) ? 1 : 2;
@@ -922,7 +955,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       mbar_wait(&B.acc_full[1], par1);
       tc_fence_after();
       CLK_MARK(EPI, 2);
-      {
+      if (keep) {
         uint32_t r0[16], r1[16];
         tmem_ld16(e.taddr + cb, r0);
         tmem_ld16(e.taddr + cb + 128, r1);
@@ -933,6 +966,8 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
           st_smem_v4(e.sA + img_off(cb + 8 * j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
           st_smem_v4(e.sA + img_off(cb + 128 + 8 * j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
         }
+      } else if (kTmemAhead) {
+        tmem_ld16(e.taddr + 256 + cb, r[0]);
       }
       fence_proxy_async_smem();
       if (st.signal) {
@@ -969,15 +1004,25 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #pragma unroll
         for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(r[cur][8 * j + t]);
         uint4 ou;
-        pq[j] = granule_fast<DT, EPI>(w, xa[ac].h[j], xb[ac].h[j], k, nbl2_2, io.in_b != nullptr, &ou);
-        if (EPI == EPI_TAN_HIDDEN) *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
+        if constexpr (kFused) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(io.wl + c + 8 * j));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(io.wl + c + 8 * j + 4));
+          const float wl[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          pq[j] = granule_fast<DT, EPI>(w, xa[ac].h[j], xb[ac].h[j], k, nbl2_2, st.signal != 0, &ou, wl, &dot);
+          if (io.out_u) stg_spill_fr(io.out_u + img_off(c + 8 * j, e.prow), ou);  // a_{L-1}: operand of the weight-gradient GEMM
+        } else {
+          pq[j] = granule_fast<DT, EPI>(w, xa[ac].h[j], xb[ac].h[j], k, nbl2_2, io.in_b != nullptr, &ou);
+          if (EPI == EPI_TAN_HIDDEN) *reinterpret_cast<uint4*>(io.out_u + img_off(c + 8 * j, e.prow)) = ou;
+        }
       }
       const uint32_t pk[8] = {pq[0].x, pq[0].y, pq[0].z, pq[0].w, pq[1].x, pq[1].y, pq[1].z, pq[1].w};
       if (io.out) {
         stg_spill_fr(io.out + img_off(c, e.prow), pq[0]);
         stg_spill_fr(io.out + img_off(c + 8, e.prow), pq[1]);
       }
-      if (half == 0) {
+      if (!keep) {
+        // forward-only fused step: the packed results are not needed by anything
+      } else if (half == 0) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
       } else {
         st_smem_v4(e.sA + img_off(c, e.prow), pq[0]);
@@ -1007,6 +1052,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
     if (io.out) *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = pk;
     st_smem_v4(e.sA + img_off(c, e.prow), pk);
   }
+  if constexpr (kFused) e.fval = dot;  // this thread's share of w_L . a_{L-1} (128 of the 512 columns)
   fence_proxy_async_smem();
   if (st.signal) {
     tc_fence_before();
@@ -1536,6 +1582,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         io.special = false;
         io.next_a = io.next_b = nullptr;
         io.cold = true;
+        io.wl = nullptr;
 #if SDF_TA_PF_DIST > 0
         if ((SW & 2) && (st.epi == EPI_TAN_HIDDEN || st.epi == EPI_ADJ_HIDDEN || st.epi == EPI_TAN_LAST)) {
           // images the next step will read (just-in-time prefetch hands over from step to step)
@@ -1562,6 +1609,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             io.vec = p.bias + l * p.H;
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_FWD_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
+          } break;
+          case EPI_FWD_FUSED: if (SW & 1) {
+            // last hidden layer + output layer (+ reverse start): see sdf_internal.h
+            io.out = (st.signal && (p.flags & FL_SPILL_Q) && !no_stg) ? img_ptr(p.Qimg, l, p.tile_stride, tile, ib) : nullptr;
+            io.out_u = ((p.flags & FL_SPILL_A) && !no_stg) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
+            io.vec = p.bias + l * p.H;
+            io.wl = p.w_last;
+            hidden_step<DT, PAR, EPI_FWD_FUSED>(e, io, k, st, B, n0, n1, gskip);
+            // f = sum of the four column-quarter partial dot products of a row + b_L (fixed order: deterministic)
+            if (e.h > 0) gskip[(e.h - 1) * kTileRows + e.prow] = e.fval;
+            named_bar_sync(1, kEpiThreads);
+            if (e.h == 0) {
+              const float f = ((e.fval + gskip[e.prow]) + gskip[kTileRows + e.prow]) + gskip[2 * kTileRows + e.prow] + __ldg(p.bias + (l + 1) * p.H);
+              e.fval = f;
+              if (e.valid && p.f_out) p.f_out[lvl_off + e.grow] = f;
+              if (e.valid && p.flag_out) p.flag_out[lvl_off + e.grow] = (p.flag_all || fabsf(f) <= p.flag_thresh) ? 1 : 0;
+            }
+            named_bar_sync(1, kEpiThreads);  // the partials live in the reverse sweep's skip buffer
           } break;
           case EPI_FWD_LAST: if (SW & 1) {
             mbar_wait(&B.acc_full[0], n0 & 1);

@@ -37,6 +37,9 @@ enum : int {
   EPI_ADJ_HIDDEN = 7,  // Zbar_l = act'(z_l) (Zbar_{l+1} W_{l+1}) + u_l               (spill Z)
   EPI_TAN_LAST = 8,    // last tangent layer fused with the adjoint start: adot_{L-1} (spill AD) and
                        // Zbar_{L-1} = act'(z_{L-1}) w_L fbar + u_{L-1} -> next A operand (spill Z); u_{L-1} never leaves the SM
+  EPI_FWD_FUSED = 9,   // last hidden forward layer fused with the output layer and the reverse start (fast mode, H = 512):
+                       // a_{L-1} (spill A), f = w_L . a_{L-1} + b_L by an in-register dot product (no N = 16 GEMM step),
+                       // q_{L-1} = w_L * act'(z_{L-1}) -> next A operand (spill Q) when a reverse sweep follows
 };
 
 struct StepDesc {
