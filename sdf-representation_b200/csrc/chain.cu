@@ -1855,7 +1855,7 @@ cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int pair, 
   if (parity) return dtype == DT_BF16 ? launch_one<DT_BF16, true, false>(p, num_sms, stream) : launch_one<DT_FP16, true, false>(p, num_sms, stream);
   // program family of this launch (api.cu builds forward [+ reverse] programs or tangent / adjoint programs)
   bool fr = false, ta = false;
-  for (int s = 0; s < p.n_steps; ++s) (p.steps[s].epi <= EPI_REV_LAST ? fr : ta) = true;
+  for (int s = 0; s < p.n_steps; ++s) ((p.steps[s].epi <= EPI_REV_LAST || p.steps[s].epi == EPI_FWD_FUSED) ? fr : ta) = true;
   if (pair) {
     if (fr && !ta) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true, 1>(p, num_sms, stream) : launch_one<DT_FP16, false, true, 1>(p, num_sms, stream);
     if (ta && !fr) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true, 2>(p, num_sms, stream) : launch_one<DT_FP16, false, true, 2>(p, num_sms, stream);

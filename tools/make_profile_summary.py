@@ -22,29 +22,35 @@ def last_json(path):
 
 b = last_json(f"{G}/bench_{tag}.json")
 r = last_json(f"{G}/bench_ref_{tag}.json")
-pcd = last_json(f"{G}/bench_pcd_{tag}.txt")
-inf = last_json(f"{G}/inference_{tag}.json")
-json.dump(inf, open(f"{P}/{tag}_inference_1xB200.json", "w"))
 k = b["roofline"]["kernel_ms_per_step"]
-out = f"""# python bench.py --steps 10 --warmup 3          (1 B200; gpurun box, clocks {b['clocks']})
-train_points_per_s {b['value']/1e6:.2f} M ({b['ms_per_step']:.2f} ms per 1M-point IGRLOSS step incl. Adam); e2e from pinned host memory {b['e2e']['ms_per_step']:.2f} ms
-whole step: {b['roofline']['whole_step']['algorithmic_tflops']:.0f} TFLOP/s algorithmic (22.03 MFLOP/point) = {100*b['roofline']['whole_step']['frac']:.1f} % of MEASURED_PEAKS bf16_tflops_sustained (1384.8)
-kernel classes, CUDA events on the launch stream, ms per step: chain fwd+rev {k['chain_fwd_rev']:.2f} | chain tan+adj {k['chain_tan_adj']:.2f} | dW {k['dw_gemm']:.2f} | other {k['other']:.2f}
-dominant kernel (tan+adj): {b['roofline']['achieved']:.0f} TFLOP/s algorithmic (2F) = {100*b['roofline']['frac']:.1f} % of sustained peak
-grid 512^3 side figure: {b['extra']['grid_queries_per_s']/1e6:.1f} M queries/s = {100*b['extra']['grid_frac_of_tensor_peak']:.1f} % of sustained peak (1F per query)
-# python bench.py --impl reference --steps 3 --warmup 1   (oracle port of the reference path, torch CPU fp32, {r['cpu_baseline']['cores']} host threads)
-{r['value']/1e3:.2f} k points/s (8192-point IGRLOSS steps, {r['ms_per_step']:.0f} ms per step)
-# python tools/bench_pcd.py                      (BASELINE config 3 per-GPU share: 1M surface + 349525 perturbed points)
-{pcd['ms_per_step']:.2f} ms per step = {pcd['surface_points_per_s']/1e6:.1f} M surface points/s = {pcd['algorithmic_tflops']:.0f} TFLOP/s algorithmic (5F per surface point) = {100*pcd['algorithmic_tflops']/1384.8:.1f} % of sustained peak
-# python tools/bench_inference.py 1024           (profiles/{tag}_inference_1xB200.json)
-1024^3 grid: {inf['grid_ms']/1e3:.2f} s on one GPU = {inf['grid_queries_per_s']/1e6:.1f} M queries/s ({100*inf['grid_frac_of_sustained_bf16_peak']:.1f} % of sustained peak); octree to level 10 (sphere, {inf['octree_queries']/1e6:.1f} M cell centres): {inf['octree_level10_ms']:.0f} ms; marching-cubes classification of 256 planes of 1024^2: {inf['mc_classify_256_planes_ms']:.1f} ms
+x = b.get("extra", {})
+par, pcd, grid, octr = x.get("train_step_parity"), x.get("pcd_train_step"), x.get("grid"), x.get("octree")
+json.dump(b, open(f"{P}/{tag}_bench_1xB200.json", "w"), indent=1)
+out = f"""# python bench.py --steps {b['steps']} --warmup {b['warmup']}          (1 B200; gpurun box, clocks {b['clocks']})
+train_points_per_s {b['value']/1e6:.2f} M ({b['ms_per_step']:.2f} ms per 1M-point IGRLOSS step incl. fused Adam); e2e from pinned host memory {b['e2e']['ms_per_step']:.2f} ms = {b['e2e']['value']/1e6:.2f} M points/s
+whole step: {b['roofline']['whole_step']['algorithmic_tflops']:.0f} TFLOP/s algorithmic (22.03 MFLOP/point) = {100*b['roofline']['whole_step']['frac']:.1f} % of MEASURED_PEAKS bf16_tflops_sustained ({b['roofline']['peak']})
+kernel classes, CUDA events on the launch stream, ms per step: chain fwd+rev {k['chain_fwd_rev']:.2f} | chain tan+adj {k['chain_tan_adj']:.2f} | dW {k['dw_gemm']:.2f} | other {k['other']:.2f} | outside kernels {b['roofline']['outside_kernels_ms_per_step']:.2f}
+dominant kernel ({b['roofline']['kernel']}): {b['roofline']['achieved']:.0f} TFLOP/s algorithmic (2F) = {100*b['roofline']['frac']:.1f} % of sustained peak; DRAM traffic per launch {('%.1f GB' % (b['roofline']['traffic']/1e9)) if b['roofline'].get('traffic') else 'n/a'} ({b['roofline']['traffic_source'][:60]})
+gpu_launches in the timed region: {b['gpu_launches']} ({b['gpu_launches']/b['steps']:.0f} per step)
+cpu_baseline: {b.get('cpu_baseline')}
+"""
+if par:
+    out += f"parity precision (hi/lo split operands, inside the 3.46e-4 tolerance): {par['ms_per_step']:.1f} ms per step = {par['points_per_s']/1e6:.2f} M points/s = {100*par['frac_of_tensor_peak_algorithmic_6F']:.1f} % of peak counting 6F algorithmic\n"
+if pcd:
+    out += f"point-cloud step (BASELINE cfg 3 share: {pcd['surface_points_per_gpu']} surface + {pcd['perturbed_points_per_gpu']} perturbed points): {pcd['ms_per_step']:.2f} ms = {pcd['surface_points_per_s']/1e6:.1f} M surface points/s = {100*pcd['frac_of_tensor_peak_algorithmic_5F']:.1f} % of peak (5F)\n"
+if grid:
+    out += f"grid {grid['n']}^3 (BASELINE cfg 4, {grid['planes_per_rank']} planes on this rank, halo {grid['halo']}): {grid['ms_grid_eval']/1e3:.3f} s = {grid['queries_per_s']/1e6:.1f} M queries/s = {100*grid['frac_of_tensor_peak']:.1f} % of peak (1F); MC classify + compact {grid['ms_mc_classify_compact']:.1f} ms ({grid['active_cells_rank0']} active cells)\n"
+if octr:
+    out += f"octree to level {octr['max_level']} (BASELINE cfg 5): {octr['ms_build']:.1f} ms for {octr['centres_total']} centres = {octr['queries_per_s']/1e6:.0f} M queries/s; cells per level {octr['cells_per_level']}\n"
+out += f"""# python bench.py --impl reference --steps 3 --warmup 1   ({r['cpu_baseline']['kind']}: {r['cpu_baseline']['sample'][:110]}, {r['cpu_baseline']['cores']} host threads)
+{r['value']/1e3:.2f} k points/s ({r['ms_per_step']:.0f} ms per 8192-point step)
 """
 open(f"{P}/{tag}_bench_1xB200.txt", "w").write(out)
 print(out)
 
 rep = f"{G}/prof_step_{tag}.ncu-rep"
 if os.path.exists(rep):
-    txt = subprocess.run([sys.executable, f"{ROOT}/tools/ncu_summary.py", rep, "12"], capture_output=True, text=True).stdout
+    txt = subprocess.run([sys.executable, f"{ROOT}/tools/ncu_summary.py", rep, "14", "--json", f"{P}/dram_bytes_per_point.json", "--points", str(b["config"]["points_per_gpu"])], capture_output=True, text=True).stdout
     open(f"{P}/{tag}_train_step_1M_ncu.txt", "w").write(txt)
 
 lst = f"{G}/launches_{tag}.csv"
@@ -63,7 +69,7 @@ if os.path.exists(lst):
         a[0] += 1
         a[1] += v
     tot = sum(v[1] for v in agg.values())
-    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-grid (1M points, 4 steps + e2e leg)",
+    lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras (1M points, 4 steps + e2e leg)",
              "# kernel | launches | total ms | share"]
     for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:14]:
         lines.append(f"{n:60s} {c:5d} {t:10.3f} {100*t/tot:6.2f} %")

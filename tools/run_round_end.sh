@@ -1,18 +1,21 @@
 #!/bin/bash
-# Round-end evidence in one GPU call: parity suite, smoke, default bench, reference arm, inference figures,
-# full-size ncu capture (one launch of each hot kernel) and launch list.   TAG=r01n bash tools/run_round_end.sh
+# Round-end evidence in one GPU call: parity suite, smoke, default bench (with every BASELINE config under "extra"),
+# reference arm, full-size ncu capture (one launch of each hot kernel) and launch list.   TAG=r02a bash tools/run_round_end.sh
 mkdir -p gpurun_out
-TAG=${TAG:-r01n}
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu_$TAG.log
+TAG=${TAG:-r02a}
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_$TAG.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cut -c1-1500 gpurun_out/bench_$TAG.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"; cat gpurun_out/bench_ref_$TAG.json
-timeout 600 python tools/bench_pcd.py > gpurun_out/bench_pcd_$TAG.txt 2>&1; tail -3 gpurun_out/bench_pcd_$TAG.txt
-timeout 900 python tools/bench_inference.py 1024 > gpurun_out/inference_$TAG.json 2> gpurun_out/inference_$TAG.err; echo "inference rc=$?"; cut -c1-700 gpurun_out/inference_$TAG.json
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-grid"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras"
 $CMD > gpurun_out/plain_full.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"chain_kernel|dw2_kernel" -s 6 -c 3 -o gpurun_out/prof_step_$TAG $CMD > gpurun_out/ncu_step.log 2>&1
 tail -1 gpurun_out/ncu_step.log
 $CMD > gpurun_out/plain_full2.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list.log 2>&1
 tail -1 gpurun_out/ncu_list.log
+if [ -n "$GRIDPROF" ]; then
+  python tools/grid_probe.py 512 > gpurun_out/grid_plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"chain_kernel" -s 2 -c 1 -o gpurun_out/prof_grid_$TAG python tools/grid_probe.py 512 > gpurun_out/ncu_grid.log 2>&1
+  tail -1 gpurun_out/ncu_grid.log
+fi
