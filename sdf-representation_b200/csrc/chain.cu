@@ -49,7 +49,7 @@ namespace sdf {
 #define CLK_MARK(kind, phase)                         \
   if (threadIdx.x == 0) {                             \
     const long long clk_t1 = clock64();               \
-    e.clk[(kind) * 8 + (phase)] += clk_t1 - clk_t0;   \
+    e.clk[((kind) == 8 ? 5 : (kind) == 9 ? 0 : (kind)) * 8 + (phase)] += clk_t1 - clk_t0;   \
     clk_t0 = clk_t1;                                  \
   }
 #else
@@ -246,7 +246,35 @@ struct Bars {
   uint64_t* acc_full;  // [2]  MMA issuer -> epilogue: accumulator half g is complete
   uint64_t* a_q;       // [4]  epilogue -> MMA issuer: A-image columns [128 j, 128 j + 128) are in place
   bool remote;         //      CTA pair, rank 1: a relay warp forwards the quarter barriers to the leader CTA
+  uint64_t* a_drain;   //      spill-store thread -> epilogue: the bulk stores of the last spilled A image have read it
 };
+// Spill images by TMA (SDF_BULK_SPILL = 1).  What the forward / reverse / tangent / adjoint epilogues spill for the
+// weight-gradient GEMM (a_l, q_l, adot_l, Zbar_l) is byte for byte the A operand image they have just written to shared
+// memory for the next layer's MMAs.  Instead of every epilogue thread also storing its 16-byte granules to global memory,
+// one thread of an otherwise idle warp issues cp.async.bulk shared -> global per completed 32 KB quarter of the image
+// and tells the epilogue (a_drain barrier) when the image may be overwritten.
+#ifndef SDF_BULK_SPILL
+#define SDF_BULK_SPILL 1
+#endif
+#ifndef SDF_BULK_SPILL_TA
+#define SDF_BULK_SPILL_TA 1
+#endif
+// before the first write to the A image after a bulk-spilled production: its copies have read shared memory
+// (drain: -1 = nothing pending, else the parity to wait for; warp-uniform)
+__device__ __forceinline__ void drain_wait(const Bars& B, int drain) {
+  if (SDF_BULK_SPILL && drain >= 0) mbar_wait(B.a_drain, static_cast<uint32_t>(drain));
+}
+#ifdef SDF_CLOCKS
+#define DRAIN_WAIT(B, d)                                                    \
+  {                                                                         \
+    const long long dw_t0 = clock64();                                      \
+    drain_wait(B, d);                                                       \
+    if (threadIdx.x == 0 && (d) >= 0) { e.clk[48] += clock64() - dw_t0; e.clk[54] += 1; } \
+  }
+#else
+#define DRAIN_WAIT(B, d) drain_wait(B, d)
+#endif
+
 // One arrival per epilogue warp on quarter barrier j (every lane has fenced its own shared-memory / TMEM accesses).
 __device__ __forceinline__ void arrive_quarter(const Bars& B, int j) {
   __syncwarp();
@@ -290,6 +318,7 @@ struct StepIO {
   const uint8_t* next_b;
   bool cold;
   const float* wl;      // EPI_FWD_FUSED: fp32 row of the output layer lin_L
+  int drain;            // bulk spill stores: parity of a_drain to wait for before the A image is overwritten (-1: none)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -685,6 +714,7 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
   mbar_wait(&B.acc_full[0], par0);
   if (st.n_groups == 2) mbar_wait(&B.acc_full[1], par1);
   tc_fence_after();
+  drain_wait(B, io.drain);
   for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
     float v[32];
     load_acc32<PAR>(e, c0, v);
@@ -730,6 +760,8 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("pre
 // has to survive in L2 for D pieces (a few microseconds) instead of up to a whole layer step: with 148 CTAs streaming
 // ~76 MB per step through a 126 MB L2, the step-start burst (D = 0) loses its late lines again before they are used
 // (round 1: DRAM reads 16 % above the operand bytes, long-scoreboard stalls on the image loads).
+// (Requesting the same lines with cp.async.bulk.prefetch.L2 from an idle warp, 64 KB per instruction and half a layer step
+// ahead, measured equal within noise -- 13.1 vs 13.2 ms -- as did D = 3, 4, 6: the sweeps are not bound by L2 misses.)
 #ifndef SDF_TA_PF_DIST
 #define SDF_TA_PF_DIST 2
 #endif
@@ -797,6 +829,7 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
         const int c0 = e.h * 32;
         tmem_ld16(e.taddr + c0, r0);
         tmem_ld16(e.taddr + c0 + 128, r1);
+        DRAIN_WAIT(B, io.drain);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -891,7 +924,7 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
   }
   CLK_MARK(EPI, 4);
 #ifdef SDF_CLOCKS
-  if (threadIdx.x == 0) e.clk[EPI * 8 + 5] += 1;
+  if (threadIdx.x == 0) e.clk[(EPI == 8 ? 5 : EPI == 9 ? 0 : EPI) * 8 + 5] += 1;
 #endif
 }
 
@@ -959,6 +992,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
         uint32_t r0[16], r1[16];
         tmem_ld16(e.taddr + cb, r0);
         tmem_ld16(e.taddr + cb + 128, r1);
+        DRAIN_WAIT(B, io.drain);
         tmem_ld_wait();
         if (kTmemAhead) tmem_ld16(e.taddr + 256 + cb, r[0]);
 #pragma unroll
@@ -1060,7 +1094,7 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
   }
   CLK_MARK(EPI, 4);
 #ifdef SDF_CLOCKS
-  if (threadIdx.x == 0) e.clk[EPI * 8 + 5] += 1;
+  if (threadIdx.x == 0) e.clk[(EPI == 8 ? 5 : EPI == 9 ? 0 : EPI) * 8 + 5] += 1;
 #endif
 }
 
@@ -1079,6 +1113,37 @@ __device__ __forceinline__ void hidden_step(Epi& e, const StepIO& io, const EpiC
   else hidden_step_plain<DT, PAR, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
   ++n0;
   if (st.n_groups == 2) ++n1;
+}
+
+// The spill image a step's epilogue produces as a copy of the A operand image it leaves in shared memory (nullptr: none).
+__device__ __forceinline__ uint8_t* step_spill_image(const ChainParams& p, const StepDesc& st, int tile, uint32_t ib) {
+  const int l = st.layer;
+  switch (st.epi) {
+    case EPI_FWD_HIDDEN: return (p.flags & FL_SPILL_A) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
+    case EPI_FWD_FUSED: return (st.signal && (p.flags & FL_SPILL_Q)) ? img_ptr(p.Qimg, l, p.tile_stride, tile, ib) : nullptr;
+    case EPI_REV_HIDDEN: return (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l - 1, p.tile_stride, tile, ib) : nullptr;
+    case EPI_TAN_HIDDEN: return img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
+    case EPI_TAN_LAST: return img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
+    case EPI_ADJ_HIDDEN: return img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
+    default: return nullptr;
+  }
+}
+// A step spills by bulk store when it runs the overlapped (staged) epilogue -- fast mode, two accumulator halves (H = 512),
+// softplus -- and the image it leaves is consumed by a GEMM (its completion is announced on the a_q barriers, which also
+// trigger the store).  The epilogue warps and the store warp evaluate the same predicate.
+template <bool PAR>
+__device__ __forceinline__ bool step_spills_by_bulk(const ChainParams& p, const StepDesc& st) {
+  if (PAR || !SDF_BULK_SPILL) return false;
+  if (st.n_groups != 2 || st.signal == 0 || (p.flags & (FL_RELU | FL_DBG_NO_STG))) return false;
+  switch (st.epi) {
+    case EPI_FWD_HIDDEN: return (p.flags & FL_SPILL_A) != 0;
+    case EPI_FWD_FUSED:
+    case EPI_REV_HIDDEN: return (p.flags & FL_SPILL_Q) != 0;
+    case EPI_TAN_HIDDEN:
+    case EPI_TAN_LAST:
+    case EPI_ADJ_HIDDEN: return SDF_BULK_SPILL_TA != 0;
+    default: return false;
+  }
 }
 
 template <bool PAIR>
@@ -1107,12 +1172,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   B.acc_full = bars + 3 * NST;            // [2]
   B.a_q = bars + 3 * NST + 2;             // [4]  this CTA's epilogue warps
   uint64_t* a_qr = bars + 3 * NST + 6;    // [4]  pair, leader only: the peer CTA's quarter is in place (one relayed arrival)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 10);
+  B.a_drain = bars + 3 * NST + 10;        //      bulk spill stores of the A image have read it (one arrival by the store thread)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 11);
   float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+#ifdef SDF_CLOCKS
+  // effective SM clock of this launch: SM cycles and global-timer nanoseconds between the start and the end of CTA 0
+  long long kclk0 = 0;
+  unsigned long long kns0 = 0;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    kclk0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(kns0));
+  }
+#endif
   B.remote = PAIR && rank != 0;
   // tiles are walked two at a time by a pair: pair i works on tiles 2i (leader) and 2i + 1 (peer); the peer of a
   // ragged last pair works on the scratch tile n_tiles (all rows invalid, images inside the even-padded arrays)
@@ -1133,6 +1208,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     }
     mbar_init(&B.acc_full[0], 1);
     mbar_init(&B.acc_full[1], 1);
+    mbar_init(B.a_drain, 1);
     for (int j = 0; j < 4; ++j) {
       mbar_init(&B.a_q[j], kEpiWarps);
       mbar_init(&a_qr[j], 1);
@@ -1342,6 +1418,60 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           }
         }
       }
+    } else if (SDF_BULK_SPILL && !PAR && warp == kMmaWarp + 2) {
+      // ------------------------------------------------------------------ spill-store thread (every CTA): one bulk copy
+      // shared -> global per completed quarter (32 KB) of the A image of every step that spills it (step_spills_by_bulk).
+      // The quarter barriers a_q[j] the epilogue warps arrive on (after their fence.proxy.async) are the trigger; a_drain
+      // tells the epilogue when quarter j may be overwritten again (the copy has read it).  Images are read back by LATER
+      // launches (kernel boundary) except the forward activations, which the reverse sweep of the same launch loads again:
+      // see out_full below.
+      if (lane == 0) {
+        const uint32_t sA_u = smem_u32(sA);
+        const uint32_t qbytes = ib / 4;
+        // Every GEMM step consumes one "production" of the A image (the tile prologue's or the previous step's), announced
+        // on a_q[0..3] with the parity of the GEMM's index.  This thread observes EVERY production in order -- a parity
+        // wait that skipped one would alias with the phase two back -- and copies out those whose step spills by bulk.
+        uint32_t n0 = 0;
+        bool any = false;  // inference programs spill nothing: this thread has nothing to pace
+        for (int s = 0; s < p.n_steps; ++s) any = any || step_spills_by_bulk<PAR>(p, p.steps[s]);
+        for (int it = it0; any && it < it_end; it += it_step) {
+          const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
+          uint8_t* out = nullptr;  // spill image of the production the next GEMM step consumes (nullptr: none)
+          bool out_full = false;
+          for (int s = 0; s < p.n_steps; ++s) {
+            const StepDesc& st = p.steps[s];
+            if (st.n_groups != 0) {
+              const uint32_t par = n0 & 1;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                mbar_wait(&B.a_q[j], par);
+                if (out) {
+                  if (SW == 2) bulk_s2g_hint(out + j * qbytes, sA_u + j * qbytes, qbytes, kPolicyEvictFirst);
+                  else bulk_s2g_u32(out + j * qbytes, sA_u + j * qbytes, qbytes);
+                  bulk_commit();
+                }
+              }
+              if (out) {
+                if (out_full) {
+                  // the last activation image before the output layer: the reverse sweep of this launch starts to read the
+                  // forward sweep's images back with generic loads -- wait until every bulk store issued so far is COMPLETE
+                  // (written and visible), fence the proxies, then release (the drain wait of the epilogue acquires)
+                  bulk_wait<0>();
+                  fence_proxy_async_all();
+                } else {
+                  bulk_wait_read<0>();  // shared memory may be overwritten as soon as the copies have READ it
+                }
+                mbar_arrive(B.a_drain);
+              }
+              ++n0;
+            }
+            out = step_spills_by_bulk<PAR>(p, st) ? step_spill_image(p, st, tile, ib) : nullptr;
+            out_full = out && st.epi == EPI_FWD_HIDDEN && s + 1 < p.n_steps &&
+                       (p.steps[s + 1].epi == EPI_FWD_FUSED || p.steps[s + 1].epi == EPI_FWD_LAST);
+          }
+        }
+        bulk_wait<0>();
+      }
     } else if (warp == kMmaWarp) {
       // ------------------------------------------------------------------ MMA issuer, CTA pair (leader CTA), lean form
       // of the loop above: M = 256 MMAs over both CTAs' tiles, 8 per weight chunk (K = 128), so the issue cost per
@@ -1390,6 +1520,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                 const uint64_t da0 = da_hi | (sA_d + kc * ((8 * 2 * kGranuleBytes) >> 4));
                 const uint64_t db0 = db_hi | (sW_d + stage * (kStage >> 4));
                 if (elect_one()) {
+#ifdef SDF_CLOCKS
+                  if (!(p.flags & FL_DBG_NO_MMA))
+#endif
 #pragma unroll
                   for (int k = 0; k < 8; ++k)
                     umma_f16_ss2(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
@@ -1494,6 +1627,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     const int inj_layer = p.skip > 0 ? p.skip - 1 : -1;
     const bool has_u = (p.flags & FL_TANGENT) && !relu;
 
+    // bulk spill stores: a_drain parity still to be waited for before the next write to the A image (-1: none), number
+    // of bulk-spilled images so far
+    int drain = -1;
+    uint32_t n_bulk = 0;
     for (int it = it0; it < it_end; it += it_step) {
           const int tile = PAIR ? 2 * it + static_cast<int>(rank) : it;
           (void)tile;
@@ -1503,6 +1640,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       // write its two granules)
       const int first = p.steps[0].epi;
       e.x[0] = e.x[1] = e.x[2] = 0.f;
+      drain_wait(B, drain);  // the input block goes into quarter 0 of the A image
+      drain = -1;
       const bool fwd_program = SW == 1 || (SW == 3 && first == EPI_FWD_HIDDEN);
       if (fwd_program) {
         if (e.math) {
@@ -1583,6 +1722,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         io.next_a = io.next_b = nullptr;
         io.cold = true;
         io.wl = nullptr;
+        // this step's spill image leaves through the store thread's bulk copies of the A image (no per-thread stores)
+        const bool bulk = step_spills_by_bulk<PAR>(p, st);
+        io.drain = drain;
+        // every step but the two N = 16 output steps and the forward-only fused end writes the A image (and waits first)
+        if (!(st.epi == EPI_FWD_LAST || st.epi == EPI_REV_LAST || (st.epi == EPI_FWD_FUSED && st.signal == 0))) drain = -1;
 #if SDF_TA_PF_DIST > 0
         if ((SW & 2) && (st.epi == EPI_TAN_HIDDEN || st.epi == EPI_ADJ_HIDDEN || st.epi == EPI_TAN_LAST)) {
           // images the next step will read (just-in-time prefetch hands over from step to step)
@@ -1605,14 +1749,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 #endif
         switch (st.epi) {
           case EPI_FWD_HIDDEN: if (SW & 1) {
-            io.out = ((p.flags & FL_SPILL_A) && !no_stg) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
+            io.out = ((p.flags & FL_SPILL_A) && !no_stg && !bulk) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
             io.vec = p.bias + l * p.H;
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_FWD_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           case EPI_FWD_FUSED: if (SW & 1) {
             // last hidden layer + output layer (+ reverse start): see sdf_internal.h
-            io.out = (st.signal && (p.flags & FL_SPILL_Q) && !no_stg) ? img_ptr(p.Qimg, l, p.tile_stride, tile, ib) : nullptr;
+            io.out = (st.signal && (p.flags & FL_SPILL_Q) && !no_stg && !bulk) ? img_ptr(p.Qimg, l, p.tile_stride, tile, ib) : nullptr;
             io.out_u = ((p.flags & FL_SPILL_A) && !no_stg) ? img_ptr(p.Aimg, l, p.tile_stride, tile, ib) : nullptr;
             io.vec = p.bias + l * p.H;
             io.wl = p.w_last;
@@ -1649,6 +1793,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           case EPI_REV_START: if (SW & 1) {
             // q_{L-1} = w_L * act'(z_{L-1}); the A image still holds a_{L-1}
             uint8_t* qimg = (p.flags & FL_SPILL_Q) ? img_ptr(p.Qimg, l, p.tile_stride, tile, ib) : nullptr;
+            drain_wait(B, io.drain);
             if (e.math) {
               for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
 #pragma unroll
@@ -1675,7 +1820,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           case EPI_REV_HIDDEN: if (SW & 1) {
             // GEMM r = q_l W_l done; q_{l-1} = r * act'(z_{l-1});  l = st.layer
             io.in_a = img_ptr(p.Aimg, l - 1, p.tile_stride, tile, ib);
-            io.out = ((p.flags & FL_SPILL_Q) && !no_stg) ? img_ptr(p.Qimg, l - 1, p.tile_stride, tile, ib) : nullptr;
+            io.out = ((p.flags & FL_SPILL_Q) && !no_stg && !bulk) ? img_ptr(p.Qimg, l - 1, p.tile_stride, tile, ib) : nullptr;
             io.special = (l - 1) == inj_layer;
             hidden_step<DT, PAR, EPI_REV_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
@@ -1706,7 +1851,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           case EPI_TAN_HIDDEN: if (SW & 2) {
             io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
             io.in_b = relu ? nullptr : img_ptr(p.Qimg, l, p.tile_stride, tile, ib);
-            io.out = no_stg ? nullptr : img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
+            io.out = (no_stg || bulk) ? nullptr : img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
             io.out_u = relu ? nullptr : img_ptr(p.Uimg, l, p.tile_stride, tile, ib);
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_TAN_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
@@ -1715,7 +1860,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             // last tangent layer + adjoint start in one epilogue: u_{L-1} is consumed where it is produced
             io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
             io.in_b = relu ? nullptr : img_ptr(p.Qimg, l, p.tile_stride, tile, ib);
-            io.out = no_stg ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
+            io.out = (no_stg || bulk) ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
             io.out_u = img_ptr(p.ADimg, l, p.tile_stride, tile, ib);
             io.vec = p.w_last;
             hidden_step<DT, PAR, EPI_TAN_LAST>(e, io, k, st, B, n0, n1, gskip);
@@ -1725,6 +1870,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             const uint8_t* aimg = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
             const uint8_t* uimg = has_u ? img_ptr(p.Uimg, l, p.tile_stride, tile, ib) : nullptr;
             uint8_t* zimg = img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
+            drain_wait(B, io.drain);
             if (e.math) {
               for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
 #pragma unroll
@@ -1762,11 +1908,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           case EPI_ADJ_HIDDEN: if (SW & 2) {
             io.in_a = img_ptr(p.Aimg, l, p.tile_stride, tile, ib);
             io.in_b = has_u ? img_ptr(p.Uimg, l, p.tile_stride, tile, ib) : nullptr;
-            io.out = no_stg ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
+            io.out = (no_stg || bulk) ? nullptr : img_ptr(p.Zimg, l, p.tile_stride, tile, ib);
             io.special = l == inj_layer;
             hidden_step<DT, PAR, EPI_ADJ_HIDDEN>(e, io, k, st, B, n0, n1, gskip);
           } break;
           default: break;
+        }
+        if (bulk) {
+          // the A image this step has left is being copied out
+          drain = static_cast<int>(n_bulk & 1);
+          ++n_bulk;
         }
       }
     }
@@ -1776,6 +1927,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 #endif
   }
 
+#ifdef SDF_CLOCKS
+  if (threadIdx.x == 0 && blockIdx.x == 0 && p.dbg_clk) {
+    unsigned long long kns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(kns1));
+    p.dbg_clk[70] = clock64() - kclk0;
+    p.dbg_clk[71] = static_cast<long long>(kns1 - kns0);
+  }
+#endif
   tc_fence_before();
   if (PAIR) cluster_sync_all();  // the peer's shared memory and TMEM stay valid until both CTAs are done
   else __syncthreads();
@@ -1839,6 +1998,9 @@ static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t st
       fprintf(stderr, "clk %-4s steps/CTA %.0f: wait_acc0 %.0f  half0 %.0f  wait_acc1 %.0f  dump %.0f  half1 %.0f\n", names[kind], n / grid,
               hb[kind * 8 + 0] / n, hb[kind * 8 + 1] / n, hb[kind * 8 + 2] / n, hb[kind * 8 + 3] / n, hb[kind * 8 + 4] / n);
     }
+    if (hb[54] > 0) fprintf(stderr, "clk DRAIN wait at the dump (thread 0): %.0f cycles per wait, %.0f waits per CTA\n", hb[48] / (double)hb[54], hb[54] / (double)grid);
+    if (hb[71] > 0)
+      fprintf(stderr, "clk KERNEL CTA 0: %.3f M cycles in %.3f ms = %.0f MHz effective SM clock\n", hb[70] / 1e6, hb[71] / 1e6, 1e3 * hb[70] / static_cast<double>(hb[71]));
     if (hb[68] > 0) {
       const double n = static_cast<double>(hb[68]);
       fprintf(stderr, "clk ISSUER per GEMM step: wait_a_lo %.0f  wait_a_hi %.0f  wait_weights %.0f  total %.0f\n", hb[64] / n, hb[65] / n, hb[66] / n, hb[67] / n);

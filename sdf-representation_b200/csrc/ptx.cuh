@@ -65,6 +65,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy encoding)
+__device__ __forceinline__ void bulk_s2g_hint(void* gmem_dst, uint32_t smem_src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_u32(void* gmem_dst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+}
+// writes of completed bulk stores (async proxy) -> visible to generic-proxy loads of threads that synchronise with this one
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
                "r"(smem_u32(smem_src)), "r"(bytes)
@@ -310,11 +321,24 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 #endif
 }
+// Wait on a barrier the peer CTA of the pair arrives on.  SDF_CLUSTER_WAIT_CTA = 1: default (.acquire.cta) semantics, the
+// form CUTLASS's ClusterBarrier::wait uses -- what the waiter consumes after these barriers (peer shared memory / TMEM) is
+// read by the tensor core through the async proxy, ordered by the peer's fence.proxy.async + tcgen05 fences, not by this
+// thread's generic loads; the .acquire.cluster form makes ptxas follow every successful wait with CCTL.IVALL, which
+// invalidates the SM's whole L1 (bias rows, lin_L row of the epilogue warps) a dozen times per layer step.
+#ifndef SDF_CLUSTER_WAIT_CTA
+#define SDF_CLUSTER_WAIT_CTA 1
+#endif
+#if SDF_CLUSTER_WAIT_CTA
+#define SDF_CLUSTER_TRY_WAIT "mbarrier.try_wait.parity.shared::cta.b64"
+#else
+#define SDF_CLUSTER_TRY_WAIT "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64"
+#endif
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      SDF_CLUSTER_TRY_WAIT " p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -341,7 +365,7 @@ __device__ __forceinline__ void mbar_wait_cluster_vote_u32(uint32_t bar_addr, ui
     if (poller) {
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          SDF_CLUSTER_TRY_WAIT " p, [%1], %2;\n\t"
           "selp.u32 %0, 1, 0, p;\n\t}"
           : "=r"(ok)
           : "r"(bar_addr), "r"(parity)
