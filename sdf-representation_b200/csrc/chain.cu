@@ -247,7 +247,22 @@ struct Bars {
   uint64_t* a_q;       // [4]  epilogue -> MMA issuer: A-image columns [128 j, 128 j + 128) are in place
   bool remote;         //      CTA pair, rank 1: a relay warp forwards the quarter barriers to the leader CTA
   uint64_t* a_drain;   //      spill-store thread -> epilogue: the bulk stores of the last spilled A image have read it
+  uint64_t* a_free;    // [2]  MMA issuer -> epilogue: the MMAs of accumulator half 1 have read A-image quarter j (j = 0, 1)
 };
+// SDF_DIRECT_A = 1: the epilogue of accumulator half 0 writes its results straight into quarters 0 / 1 of the A image as
+// soon as the MMAs of half 1 -- which walk the K quarters in order -- have read them (a_free[j], committed by the issuer
+// after the quarter's last weight chunk).  Round-1 form (0): half 0 parks its packed results in the TMEM columns it has
+// consumed and moves them to shared memory after half 1's MMAs have completed ("dump": 0.75-1.3 k cycles per layer step on
+// the critical path of a kernel whose critical path is the epilogue, plus 64 KB of tcgen05.st + tcgen05.ld per step).
+// Measured (same-session A/B, 1M-point step): forward + reverse 9.40 -> 8.84 ms, 1024^3-class grid inference 321 -> 329 M
+// queries/s; tangent + adjoint 13.2 -> 13.7 ms (its half-0 epilogue waits for HBM operands anyway and then collides with the
+// a_free waits), so that family keeps the parked form (SDF_DIRECT_A_TA = 0).
+#ifndef SDF_DIRECT_A
+#define SDF_DIRECT_A 1
+#endif
+#ifndef SDF_DIRECT_A_TA
+#define SDF_DIRECT_A_TA 0
+#endif
 // Spill images by TMA (SDF_BULK_SPILL = 1).  What the forward / reverse / tangent / adjoint epilogues spill for the
 // weight-gradient GEMM (a_l, q_l, adot_l, Zbar_l) is byte for byte the A operand image they have just written to shared
 // memory for the next layer's MMAs.  Instead of every epilogue thread also storing its 16-byte granules to global memory,
@@ -256,8 +271,10 @@ struct Bars {
 #ifndef SDF_BULK_SPILL
 #define SDF_BULK_SPILL 1
 #endif
+// tangent / adjoint programs: off -- measured 14.2-14.5 vs 13.0-13.3 ms with the bulk stores (the kernel is HBM-bound;
+// 32 KB store bursts serve it worse than the per-thread stores that are spread over the pieces)
 #ifndef SDF_BULK_SPILL_TA
-#define SDF_BULK_SPILL_TA 1
+#define SDF_BULK_SPILL_TA 0
 #endif
 // before the first write to the A image after a bulk-spilled production: its copies have read shared memory
 // (drain: -1 = nothing pending, else the parity to wait for; warp-uniform)
@@ -819,29 +836,44 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     if (half == 1) {
-      tmem_st_wait();
-      CLK_MARK(EPI, 1);
-      mbar_wait(&B.acc_full[1], par1);
-      tc_fence_after();
-      CLK_MARK(EPI, 2);
-      {
-        uint32_t r0[16], r1[16];
-        const int c0 = e.h * 32;
-        tmem_ld16(e.taddr + c0, r0);
-        tmem_ld16(e.taddr + c0 + 128, r1);
-        DRAIN_WAIT(B, io.drain);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          st_smem_v4(e.sA + img_off(c0 + 8 * j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
-          st_smem_v4(e.sA + img_off(c0 + 128 + 8 * j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
+      if (SDF_DIRECT_A_TA) {
+        // half 0 went straight into quarters 0 / 1 of the A image: release them (the next GEMM may start on K < 256 and
+        // overwrite accumulator half 0, which this thread has finished reading)
+        fence_proxy_async_smem();
+        if (st.signal) {
+          tc_fence_before();
+          arrive_quarter(B, 0);
+          arrive_quarter(B, 1);
         }
-      }
-      fence_proxy_async_smem();
-      if (st.signal) {
-        tc_fence_before();
-        arrive_quarter(B, 0);
-        arrive_quarter(B, 1);
+        CLK_MARK(EPI, 1);
+        mbar_wait(&B.acc_full[1], par1);
+        tc_fence_after();
+        CLK_MARK(EPI, 2);
+      } else {
+        tmem_st_wait();
+        CLK_MARK(EPI, 1);
+        mbar_wait(&B.acc_full[1], par1);
+        tc_fence_after();
+        CLK_MARK(EPI, 2);
+        {
+          uint32_t r0[16], r1[16];
+          const int c0 = e.h * 32;
+          tmem_ld16(e.taddr + c0, r0);
+          tmem_ld16(e.taddr + c0 + 128, r1);
+          if (SDF_BULK_SPILL_TA) DRAIN_WAIT(B, io.drain);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st_smem_v4(e.sA + img_off(c0 + 8 * j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
+            st_smem_v4(e.sA + img_off(c0 + 128 + 8 * j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
+          }
+        }
+        fence_proxy_async_smem();
+        if (st.signal) {
+          tc_fence_before();
+          arrive_quarter(B, 0);
+          arrive_quarter(B, 1);
+        }
       }
       CLK_MARK(EPI, 3);
     }
@@ -904,12 +936,17 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
         stg_spill(io.out + img_off(c, e.prow), p0);
         stg_spill(io.out + img_off(c + 8, e.prow), p1);
       }
-      if (half == 0) {
+      if (half == 0 && !SDF_DIRECT_A_TA) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
       } else {
+        if (half == 0) {
+          // quarter pc / 2 of the A image: the MMAs of accumulator half 1 have read it
+          if (pc == 0 && SDF_BULK_SPILL_TA) DRAIN_WAIT(B, io.drain);
+          if ((pc & 1) == 0) mbar_wait(&B.a_free[pc >> 1], par1);
+        }
         st_smem_v4(e.sA + img_off(c, e.prow), p0);
         st_smem_v4(e.sA + img_off(c + 8, e.prow), p1);
-        if (pc == 1) {
+        if (half == 1 && pc == 1) {
           // this thread's share of A columns [256,384) is written: the next GEMM may run two more weight chunks
           fence_proxy_async_smem();
           if (st.signal) arrive_quarter(B, 2);
@@ -983,31 +1020,46 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #pragma unroll kUnrollHalves
   for (int half = 0; half < 2; ++half) {
     if (half == 1) {
-      tmem_st_wait();
-      CLK_MARK(EPI, 1);
-      mbar_wait(&B.acc_full[1], par1);
-      tc_fence_after();
-      CLK_MARK(EPI, 2);
-      if (keep) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(e.taddr + cb, r0);
-        tmem_ld16(e.taddr + cb + 128, r1);
-        DRAIN_WAIT(B, io.drain);
-        tmem_ld_wait();
-        if (kTmemAhead) tmem_ld16(e.taddr + 256 + cb, r[0]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          st_smem_v4(e.sA + img_off(cb + 8 * j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
-          st_smem_v4(e.sA + img_off(cb + 128 + 8 * j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
+      if (SDF_DIRECT_A) {
+        // half 0 went straight into quarters 0 / 1 of the A image: release them
+        fence_proxy_async_smem();
+        if (st.signal) {
+          tc_fence_before();
+          arrive_quarter(B, 0);
+          arrive_quarter(B, 1);
         }
-      } else if (kTmemAhead) {
-        tmem_ld16(e.taddr + 256 + cb, r[0]);
-      }
-      fence_proxy_async_smem();
-      if (st.signal) {
-        tc_fence_before();
-        arrive_quarter(B, 0);
-        arrive_quarter(B, 1);
+        CLK_MARK(EPI, 1);
+        mbar_wait(&B.acc_full[1], par1);
+        tc_fence_after();
+        CLK_MARK(EPI, 2);
+        if (kTmemAhead) tmem_ld16(e.taddr + 256 + cb, r[0]);
+      } else {
+        tmem_st_wait();
+        CLK_MARK(EPI, 1);
+        mbar_wait(&B.acc_full[1], par1);
+        tc_fence_after();
+        CLK_MARK(EPI, 2);
+        if (keep) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(e.taddr + cb, r0);
+          tmem_ld16(e.taddr + cb + 128, r1);
+          DRAIN_WAIT(B, io.drain);
+          tmem_ld_wait();
+          if (kTmemAhead) tmem_ld16(e.taddr + 256 + cb, r[0]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st_smem_v4(e.sA + img_off(cb + 8 * j, e.prow), make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]));
+            st_smem_v4(e.sA + img_off(cb + 128 + 8 * j, e.prow), make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]));
+          }
+        } else if (kTmemAhead) {
+          tmem_ld16(e.taddr + 256 + cb, r[0]);
+        }
+        fence_proxy_async_smem();
+        if (st.signal) {
+          tc_fence_before();
+          arrive_quarter(B, 0);
+          arrive_quarter(B, 1);
+        }
       }
       CLK_MARK(EPI, 3);
     }
@@ -1056,12 +1108,17 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
       }
       if (!keep) {
         // forward-only fused step: the packed results are not needed by anything
-      } else if (half == 0) {
+      } else if (half == 0 && !SDF_DIRECT_A) {
         tmem_st8(e.taddr + c0 + (pc & 1) * 8, pk);  // park: columns [c0, c0+16) hold the chunk's 32 packed results
       } else {
+        if (half == 0) {
+          // quarter pc / 2 of the A image: the MMAs of accumulator half 1 have read it
+          if (pc == 0) DRAIN_WAIT(B, io.drain);
+          if ((pc & 1) == 0) mbar_wait(&B.a_free[pc >> 1], par1);
+        }
         st_smem_v4(e.sA + img_off(c, e.prow), pq[0]);
         st_smem_v4(e.sA + img_off(c + 8, e.prow), pq[1]);
-        if (pc == 1) {
+        if (half == 1 && pc == 1) {
           // this thread's share of A columns [256,384) is written: the next GEMM may run two more weight chunks
           fence_proxy_async_smem();
           if (st.signal) arrive_quarter(B, 2);
@@ -1173,12 +1230,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   B.a_q = bars + 3 * NST + 2;             // [4]  this CTA's epilogue warps
   uint64_t* a_qr = bars + 3 * NST + 6;    // [4]  pair, leader only: the peer CTA's quarter is in place (one relayed arrival)
   B.a_drain = bars + 3 * NST + 10;        //      bulk spill stores of the A image have read it (one arrival by the store thread)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 11);
+  B.a_free = bars + 3 * NST + 11;         // [2]  accumulator half 1's MMAs have read A-image quarter 0 / 1 (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 13);
   float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // this instantiation can contain steps that spill by bulk store (see step_spills_by_bulk)
+  constexpr bool kBulkK = SDF_BULK_SPILL && !PAR && ((SW & 1) != 0 || SDF_BULK_SPILL_TA);
 #ifdef SDF_CLOCKS
   // effective SM clock of this launch: SM cycles and global-timer nanoseconds between the start and the end of CTA 0
   long long kclk0 = 0;
@@ -1209,6 +1269,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     mbar_init(&B.acc_full[0], 1);
     mbar_init(&B.acc_full[1], 1);
     mbar_init(B.a_drain, 1);
+    mbar_init(&B.a_free[0], 1);
+    mbar_init(&B.a_free[1], 1);
     for (int j = 0; j < 4; ++j) {
       mbar_init(&B.a_q[j], kEpiWarps);
       mbar_init(&a_qr[j], 1);
@@ -1284,7 +1346,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       // warp-uniform (uniform registers) and one elected lane issues.
       const uint32_t sA_d = smem_u32(sA) >> 4, sW_d = smem_u32(sW) >> 4;  // descriptor start-address units (16 B)
       const uint32_t wfull_u = smem_u32(w_full), wempty_u = smem_u32(w_empty);
-      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q);
+      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q), afree_u = smem_u32(B.a_free);
       uint32_t stage = 0, wpar = 0, n0 = 0;
       const bool poller = elect_one();  // (opaque to the compiler: a predicate it keeps instead of re-deriving the lane)
       for (int it = it0; it < it_end; it += it_step) {
@@ -1334,6 +1396,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                                   (kc | k) != 0 ? 1u : 0u);
                   }
                   umma_commit_u32(wempty_u + 8 * stage);
+                  if (g == 1 && (kc == 1 || kc == 3)) umma_commit_u32(afree_u + 8 * (kc >> 1));  // K quarter kc / 2 has been read
                   if (kc == 7) umma_commit_u32(accfull_u + 8 * g);
                 }
                 __syncwarp();
@@ -1387,7 +1450,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                   }
                 }
                 umma_commit_u32(wempty_u + 8 * stage);
-                if (kc + 1 == kchunks) umma_commit_u32(accfull_u + 8 * g);
+                if (kc + 1 == kchunks) {
+                  if (g == 1) { umma_commit_u32(afree_u); umma_commit_u32(afree_u + 8); }  // other shapes: with the group's last chunk
+                  umma_commit_u32(accfull_u + 8 * g);
+                }
               }
               __syncwarp();
               a_d += a_chunk_d;
@@ -1418,7 +1484,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           }
         }
       }
-    } else if (SDF_BULK_SPILL && !PAR && warp == kMmaWarp + 2) {
+    } else if (kBulkK && warp == kMmaWarp + 2) {
       // ------------------------------------------------------------------ spill-store thread (every CTA): one bulk copy
       // shared -> global per completed quarter (32 KB) of the A image of every step that spills it (step_spills_by_bulk).
       // The quarter barriers a_q[j] the epilogue warps arrive on (after their fence.proxy.async) are the trigger; a_drain
@@ -1479,7 +1545,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       // tensor time.
       const uint32_t sA_d = smem_u32(sA) >> 4, sW_d = smem_u32(sW) >> 4;
       const uint32_t wfull_u = smem_u32(w_full), wempty_u = smem_u32(w_empty), pfull_u = smem_u32(peer_full);
-      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q), aqr_u = smem_u32(a_qr);
+      const uint32_t accfull_u = smem_u32(B.acc_full), aq_u = smem_u32(B.a_q), aqr_u = smem_u32(a_qr), afree_u = smem_u32(B.a_free);
       uint32_t stage = 0, wpar = 0, n0 = 0;
       const bool poller = elect_one();
       for (int it = it0; it < it_end; it += it_step) {
@@ -1528,6 +1594,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                     umma_f16_ss2(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
                                  (kc | k) != 0 ? 1u : 0u);
                   umma_commit2_u32(wempty_u + 8 * stage, 3);
+                  if (g == 1 && kc < 2) umma_commit2_u32(afree_u + 8 * kc, 3);  // K quarter kc of both A images has been read
                   if (kc == 3) umma_commit2_u32(accfull_u + 8 * g, 3);
                 }
                 __syncwarp();
@@ -1568,7 +1635,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                   umma_f16_ss2(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc,
                                (kc | k) != 0 ? 1u : 0u);
                 umma_commit2_u32(wempty_u + 8 * stage, 3);
-                if (kc + 1 == kchunks) umma_commit2_u32(accfull_u + 8 * g, 3);
+                if (kc + 1 == kchunks) {
+                  if (g == 1) { umma_commit2_u32(afree_u, 3); umma_commit2_u32(afree_u + 8, 3); }
+                  umma_commit2_u32(accfull_u + 8 * g, 3);
+                }
               }
               __syncwarp();
               a_d += a_chunk_d;
@@ -1723,8 +1793,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         io.cold = true;
         io.wl = nullptr;
         // this step's spill image leaves through the store thread's bulk copies of the A image (no per-thread stores)
-        const bool bulk = step_spills_by_bulk<PAR>(p, st);
-        io.drain = drain;
+        const bool bulk = kBulkK && step_spills_by_bulk<PAR>(p, st);
+        io.drain = kBulkK ? drain : -1;
         // every step but the two N = 16 output steps and the forward-only fused end writes the A image (and waits first)
         if (!(st.epi == EPI_FWD_LAST || st.epi == EPI_REV_LAST || (st.epi == EPI_FWD_FUSED && st.signal == 0))) drain = -1;
 #if SDF_TA_PF_DIST > 0
