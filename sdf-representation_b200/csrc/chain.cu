@@ -785,19 +785,10 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("pre
 #ifndef SDF_PF_EL
 #define SDF_PF_EL 0
 #endif
-#ifndef SDF_PF_L1
-#define SDF_PF_L1 0
-#endif
 __device__ __forceinline__ void prefetch_l2_hint(const void* ptr) {
-  if (SDF_PF_L1) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-  else if (SDF_PF_EL) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ptr));
+  if (SDF_PF_EL) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ptr));
   else asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
-// SDF_TA_A_AHEAD = 1 (tangent / adjoint loop form): the activation words of piece p + 1 are requested while piece p is
-// processed (8 registers), the q / u words of a piece when it starts -- they are consumed last in the piece's arithmetic.
-#ifndef SDF_TA_A_AHEAD
-#define SDF_TA_A_AHEAD 0
-#endif
 // first column of piece P (0..7) of a 512-wide step for this thread: half P / 4, chunk (P / 2) % 2, sub-piece P % 2
 __device__ __forceinline__ int piece_col(const Epi& e, int P) { return (P >> 2) * 256 + ((P >> 1) & 1) * 128 + e.h * 32 + (P & 1) * 16; }
 __device__ __forceinline__ void prefetch_piece(const Epi& e, const uint8_t* a, const uint8_t* b, int P) {
@@ -900,14 +891,7 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
         else if (io.next_a) prefetch_piece(e, io.next_a, io.next_b, T - 8);
       }
 #endif
-#if SDF_TA_A_AHEAD
-      Piece<false> xa_next;
-      {
-        if ((pc > 0 || half == 1) && io.in_b) ldg_piece<false>(e, c, io.in_b, xb);
-        const int cn = pc < 3 ? half * 256 + ((pc + 1) >> 1) * 128 + e.h * 32 + ((pc + 1) & 1) * 16 : 256 + e.h * 32;
-        if (pc < 3 || half == 0) ldg_piece<false>(e, cn, io.in_a, xa_next);
-      }
-#elif defined(SDF_CLOCKS)
+#ifdef SDF_CLOCKS
       if ((pc > 0 || half == 1) && !k.no_aux) load_aux<false, EPI>(e, io, c, xa, xb);
 #else
       if (pc > 0 || half == 1) load_aux<false, EPI>(e, io, c, xa, xb);
@@ -968,9 +952,6 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
           if (st.signal) arrive_quarter(B, 2);
         }
       }
-#if SDF_TA_A_AHEAD
-      if (pc < 3 || half == 0) xa = xa_next;
-#endif
     }
   }
   fence_proxy_async_smem();
