@@ -504,3 +504,63 @@ def test_two_rank_nccl_sharded_step_equals_single(tmp_path):
         assert abs(out[name]["loss"] - out[name]["loss_ref"]) < 2e-6 * max(1.0, abs(out[name]["loss_ref"])), name
         # fp32 atomics in a different order + different tile composition: not bit-equal, far below the mode's tolerance
         assert out[name]["grad_rel"] < 2e-3, name
+
+
+def test_dataparallel_wrapped_model_runs_the_fused_path():
+    """executor/executor.py:53-56 wraps the model in nn.DataParallel when more than one GPU is visible.  Old scripts that
+    still do so keep working: the losses unwrap ``.module`` (one fused step on the module's device, no replication), the
+    result equals the bare module's bit for bit, and ``model(x)`` through the wrapper reaches the CUDA forward."""
+    import sdf_representation_b200 as pkg
+
+    d = load_golden("round2_128x4.npz")
+    x, y = torch.from_numpy(d["x"]).to(dev()), torch.from_numpy(d["y"]).to(dev())
+    bare = small_net(d, "parity")
+    wrapped = torch.nn.DataParallel(small_net(d, "parity"), device_ids=[0])
+    crit = pkg.IGRLOSS(0.1, 1.0, 0.1, 0.05)
+    l0 = crit(x, y, bare, 0)
+    l0.backward()
+    l1 = crit(x, y, wrapped, 0)
+    l1.backward()
+    assert float(l0) == float(l1)
+    for p0, p1 in zip(bare.parameters(), wrapped.module.parameters()):
+        assert p1.grad is not None and rel_err(p1.grad.cpu(), p0.grad.cpu()) < 1e-5  # split-K order: not bit-identical
+    with torch.no_grad():
+        f0, f1 = bare(x), wrapped(x)
+    assert torch.equal(f0, f1)
+    assert pkg.compute_normal(wrapped, x.clone()).shape == (x.shape[0], 3)
+
+
+def test_training_step_repeats_are_bit_identical_under_stress():
+    """The spill images of the forward / reverse sweeps leave by bulk copies of the A image (spill-store warp, a_q trigger,
+    a_drain release) and accumulator half 0 is written into A-image quarters as the MMAs free them (a_free): a copy that
+    read a quarter too late, or an epilogue that overwrote one too early, would change what the reverse sweep / the
+    weight-gradient GEMM read back.  150 repeats of the deterministic 8 x 512 step over ~4 tile pairs per SM pair (ragged
+    tile count) must give the same bits every time: loss, f, grad f and all 1.84 M parameter gradients."""
+    import sdf_representation_b200 as pkg
+
+    g = torch.Generator().manual_seed(7)
+    x = (torch.rand(148 * 128 * 4 + 333, 3, generator=g) * 2 - 1).to(dev())
+    y = orc.torus_labels(x.cpu()).float().to(dev())
+    torch.manual_seed(0)
+    net = pkg.ImplicitNet(3, [512] * 8, (4,), 100.0, True, precision="fast", deterministic=True).to(dev())
+    crit = pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0)
+    params = list(net.parameters())
+
+    def run():
+        for p in params:
+            p.grad = None
+        loss = crit(x, y, net, 0)
+        loss.backward()
+        return torch.cat([loss.detach().reshape(1)] + [p.grad.reshape(-1) for p in params]).clone()
+
+    ref = run()
+    bad = torch.zeros((), dtype=torch.int64, device=dev())
+    for _ in range(150):
+        bad += (run() != ref).sum()
+    assert int(bad) == 0
+    f0, g0 = net.sdf_and_gradient(x)
+    f0, g0 = f0.clone(), g0.clone()
+    for _ in range(50):
+        f1, g1 = net.sdf_and_gradient(x)
+        bad += (f1 != f0).sum() + (g1 != g0).sum()
+    assert int(bad) == 0
