@@ -14,6 +14,13 @@
 
 namespace sdf {
 
+// Split-K partial sums meet in the fp32 gradient accumulator: a reduction without return value on a pointer that is known
+// to be global memory (atomicAdd on the generic pointer of a DwItem compiles to ATOM + a shared-memory CAS-spin fallback
+// behind a QSPC branch; this is one RED.E.ADD.F32 per element).
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+
 constexpr int kDwStages = 2;
 constexpr int kDwThreads = 192;
 constexpr uint32_t kDwABytes = 16 * kGranuleBytes;   // 128 features x 128 points
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwItem* __restr
           for (int j = 0; j < 16; ++j) {
             float* o = d.out + static_cast<size_t>(c0 + j) * d.out_ld + m;
             if (d.store) *o = __uint_as_float(r[j]) * im;
-            else atomicAdd(o, __uint_as_float(r[j]) * im);
+            else red_add_f32(o, __uint_as_float(r[j]) * im);
           }
         }
       }
@@ -382,7 +389,7 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity, int* __res
           for (int j = 0; j < 16; ++j) {
             float* o = d.out + static_cast<size_t>(c0 + j) * d.out_ld + m;
             if (d.store) *o = __uint_as_float(r[j]) * im;
-            else atomicAdd(o, __uint_as_float(r[j]) * im);
+            else red_add_f32(o, __uint_as_float(r[j]) * im);
           }
         }
         if (d.out_x) {
@@ -393,7 +400,7 @@ dw2_kernel(const DwItem* __restrict__ items, int n_items, int parity, int* __res
           for (int j = 0; j < 16; ++j) {
             float* o = d.out_x + static_cast<size_t>(j) * d.out_ld + m;
             if (d.store) *o = __uint_as_float(r[j]) * im;
-            else atomicAdd(o, __uint_as_float(r[j]) * im);
+            else red_add_f32(o, __uint_as_float(r[j]) * im);
           }
         }
       }
