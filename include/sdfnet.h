@@ -132,6 +132,16 @@ int sdfnet_fused_adam_step(sdfnet_t h, float* const* weights, float* const* bias
                            float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* grad_scale_dev,
                            float* grads_out, void* stream);
 
+/* model/losses.py:50-69 WeightedSmoothL2Loss(weight_factor, delta) -- the loss the shipped ini selects -- as one fused
+ * first-order step: forward, seeds, adjoint sweep, weight gradients into the accumulators; loss_sums[8] (double, device) +=
+ * {sum p, sum p^2, sum w (t-p)^2, sum w, sum w t, sum w t^2, 0, count} of this shard.  label_stats_dev = DEVICE
+ * {sum w, sum w t, sum w t^2, N} over the whole (multi-GPU) batch (sdfnet_wsl2_label_stats + cross-rank sum).  data_term
+ * 0 = the reference's [N,1] - [N] broadcast mean in closed form, 1 = per-point mean(w (t - p)^2). */
+int sdfnet_wsl2_label_stats(const float* y, int64_t n, float delta, float weight_factor, double* out4, void* stream);
+int sdfnet_train_step_wsl2(sdfnet_t h, const float* x, const float* y, int64_t n, float delta, float weight_factor,
+                           int32_t data_term, const double* label_stats_dev, double* loss_sums, void* ws, size_t ws_bytes,
+                           void* stream);
+
 /* Reproducibility switch (the reference's cuBLAS SGEMM + ATen path gives the same bits on every run; the default
  * split-K red.add of the weight-gradient GEMM does not).  on != 0: every split of a dW block stores into a private slot
  * and a second pass adds the slots in split order; the loss sums go through per-block partials added in block order.
@@ -151,7 +161,8 @@ int sdfnet_grad_buffer(sdfnet_t h, float** buf, int64_t* n_floats);
 
 /* Loss value of the last step(s) from the tail of the gradient buffer (after the cross-rank sum): out4 (device) =
  * {total, term0, term1, term2}; n_global <= 0: the point count that travelled with the sums.  kind 0: IGRLOSS model/losses.py:118-136 {data, normal, eikonal};
- * kind 1: point-cloud loss executor/executordistributed.py:73-79 {surface, eikonal, 0}. */
+ * kind 1: point-cloud loss executor/executordistributed.py:73-79 {surface, eikonal, 0}; kind 2: WeightedSmoothL2Loss
+ * model/losses.py:50-69 {value, 0, 0}. */
 int sdfnet_loss_value(sdfnet_t h, int32_t kind, float tau, float lambda_g, int32_t data_term, int64_t n_global, int64_t m_global,
                       float* out4, void* stream);
 

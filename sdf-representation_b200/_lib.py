@@ -67,6 +67,11 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "sdfnet_wsl2_label_stats": (c_int32, [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "sdfnet_train_step_wsl2": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
     "sdfnet_adam_step": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32, c_void_p],

@@ -23,6 +23,10 @@ cudaError_t launch_label_stats(const float* y, int64_t n, float delta, double* o
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
                              unsigned* absmax, float* fbar, float* gbar, double* sums, double* fbar_sum, double* part,
                              cudaStream_t stream);
+cudaError_t launch_wsl2_label_stats(const float* y, int64_t n, float delta, float wf, double* out4, cudaStream_t stream);
+cudaError_t launch_wsl2_seeds(const float* f, const float* y, int64_t n, float delta, float wf, int data_term, const double* stats,
+                              int relu_tanh, unsigned* absmax, float* fbar, double* sums, double* fbar_sum, double* part,
+                              cudaStream_t stream);
 cudaError_t launch_absmax(const float* v, int64_t n, unsigned* absmax, cudaStream_t stream);
 cudaError_t launch_seed_scale(unsigned* absmax, float* scale, const double* sums, const double* fbar_sum, float* tail,
                               cudaStream_t stream);
@@ -1028,6 +1032,43 @@ extern "C" int sdfnet_train_step_pcd(sdfnet_t h, const float* x, int64_t n, int6
   return 0;
 }
 
+extern "C" int sdfnet_wsl2_label_stats(const float* y, int64_t n, float delta, float weight_factor, double* out4, void* stream_) {
+  if (!y || !out4) return fail(1, "sdfnet_wsl2_label_stats: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CU(cudaMemsetAsync(out4, 0, 4 * sizeof(double), stream));
+  if (n > 0) CU(launch_wsl2_label_stats(y, n, delta, weight_factor, out4, stream));
+  return 0;
+}
+
+// model/losses.py:50-69 WeightedSmoothL2Loss as one fused first-order step: forward (spills a_l) -> seeds + loss sums ->
+// adjoint sweep -> first term of the weight-gradient GEMMs (3F per point; the generic autograd path runs the forward twice)
+extern "C" int sdfnet_train_step_wsl2(sdfnet_t h, const float* x, const float* y, int64_t n, float delta, float weight_factor,
+                                      int32_t data_term, const double* label_stats_dev, double* loss_sums, void* ws_, size_t ws_bytes,
+                                      void* stream_) {
+  if (!h || !x || !y || !label_stats_dev || !loss_sums) return fail(1, "sdfnet_train_step_wsl2: null argument");
+  if (data_term != 0 && data_term != 1) return fail(1, "sdfnet_train_step_wsl2: data_term must be 0 (pairwise) or 1 (pointwise)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* ws = align_ws(ws_, ws_bytes);
+  const int64_t chunk = ws_ ? chunk_points(h, ws_bytes) : 0;
+  if (chunk <= 0) return fail(1, "sdfnet_train_step_wsl2: workspace too small (%zu bytes, need >= %zu per 128 points)", ws_bytes, per_tile_bytes(h, 1));
+  for (int64_t o = 0; o < n; o += chunk) {
+    const int64_t m = n - o < chunk ? n - o : chunk;
+    const int tiles = static_cast<int>((m + h->pts - 1) / h->pts);
+    Spill s;
+    carve(h, 1, ws, tiles, s);
+    if (int rc = run_fg(h, x + o * 3, m, s, false, stream)) return rc;
+    {
+      Launch ls(h, PC_OTHER, stream, 2);
+      CU(launch_wsl2_seeds(s.f, y + o * 4, m, delta, weight_factor, data_term, label_stats_dev, h->relu ? 1 : 0, h->absmax_dev, s.fbar,
+                           loss_sums, h->fbar_sum, h->deterministic ? h->det_part : nullptr, stream));
+      CU(launch_seed_scale(h->absmax_dev, h->scale_dev, loss_sums, h->fbar_sum, h->tail, stream));
+    }
+    if (int rc = run_ta(h, m, s, s.fbar, nullptr, stream)) return rc;
+    if (int rc = run_dw(h, s, tiles, false, stream)) return rc;
+  }
+  return 0;
+}
+
 extern "C" int sdfnet_set_deterministic(sdfnet_t h, int32_t on) {
   if (!h) return fail(1, "sdfnet_set_deterministic: null handle");
   if (on && !h->det_part) CU(cudaMalloc(&h->det_part, sizeof(double) * kDetBlocks * 16));
@@ -1053,7 +1094,7 @@ extern "C" int sdfnet_grad_buffer(sdfnet_t h, float** buf, int64_t* n_floats) {
 extern "C" int sdfnet_loss_value(sdfnet_t h, int32_t kind, float tau, float lambda_g, int32_t data_term, int64_t n_global,
                                  int64_t m_global, float* out4, void* stream) {
   if (!h || !out4) return fail(1, "sdfnet_loss_value: null argument");
-  if (kind != 0 && kind != 1) return fail(1, "sdfnet_loss_value: kind must be 0 (IGRLOSS) or 1 (point cloud)");
+  if (kind < 0 || kind > 2) return fail(1, "sdfnet_loss_value: kind must be 0 (IGRLOSS), 1 (point cloud) or 2 (WeightedSmoothL2Loss)");
   Launch ll(h, PC_OTHER, static_cast<cudaStream_t>(stream));
   CU(launch_loss_value(h->tail, kind, tau, lambda_g, data_term, n_global > 0 ? 1.0 / static_cast<double>(n_global) : 0.0,
                        m_global > 0 ? 1.0 / static_cast<double>(m_global) : 0.0, out4, static_cast<cudaStream_t>(stream)));

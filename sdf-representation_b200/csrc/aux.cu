@@ -195,6 +195,53 @@ __global__ void pcd_seeds_kernel(const float* __restrict__ f, const float* __res
   block_accumulate<1>(fsum, fbar_sum, part, 2, 1);
 }
 
+// reference model/losses.py:50-69 WeightedSmoothL2Loss (the loss the shipped ini selects): t = clamp(S, +-delta),
+// p = clamp(f, +-delta), w = 1 + wf exp(-|t|).  The reference's [N,1] - [N] broadcast makes it mean_{i,j} w_j (t_j - p_i)^2
+// = mean(w t^2) - 2 mean(p) mean(w t) + mean(p^2) mean(w)  ("pairwise", data_term 0); data_term 1 = mean(w (t - p)^2).
+// Label moments {sum w, sum w t, sum w t^2, N} of one shard (summed over ranks before the seeds):
+__global__ void wsl2_label_stats_kernel(const float* __restrict__ y, long n, float delta, float wf, double* __restrict__ out4) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float t = fminf(fmaxf(__ldg(y + 4 * i), -delta), delta);
+    const float w = 1.f + wf * expf(-fabsf(t));
+    acc[0] += w; acc[1] += w * t; acc[2] += w * t * t; acc[3] += 1.f;
+  }
+  block_accumulate<4>(acc, out4);
+}
+// Seeds: d L / d f_i = [|f_i| <= delta] (2/N) (p_i mean(w) - mean(w t))  (pairwise)  |  (2/N) w_i (p_i - t_i)  (pointwise);
+// no gradient term.  sums += {sum p, sum p^2, sum w (t-p)^2, sum w, sum w t, sum w t^2, 0, count} of this shard.
+__global__ void wsl2_seeds_kernel(const float* __restrict__ f, const float* __restrict__ y, long n, float delta, float wf, int data_term,
+                                  const double* __restrict__ stats, int relu_tanh, unsigned* __restrict__ absmax,
+                                  float* __restrict__ fbar, double* __restrict__ sums, double* __restrict__ fbar_sum,
+                                  double* __restrict__ part) {
+  const double ng = stats[3];
+  const float inv_n = ng > 0.0 ? static_cast<float>(1.0 / ng) : 0.f;
+  const float mean_w = static_cast<float>(stats[0] * (ng > 0.0 ? 1.0 / ng : 0.0));
+  const float mean_wt = static_cast<float>(stats[1] * (ng > 0.0 ? 1.0 / ng : 0.0));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float fsum[1] = {0.f};
+  float amax = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float fi = f[i];
+    const float pi = fminf(fmaxf(fi, -delta), delta);
+    const float t = fminf(fmaxf(__ldg(y + 4 * i), -delta), delta);
+    const float w = 1.f + wf * expf(-fabsf(t));
+    const bool inside = fi >= -delta && fi <= delta;  // torch.clamp passes the gradient on the closed interval
+    float fb = data_term == 0 ? 2.f * inv_n * (pi * mean_w - mean_wt) : 2.f * inv_n * w * (pi - t);
+    if (!inside) fb = 0.f;
+    if (relu_tanh) fb *= 1.f - fi * fi;  // f = tanh(z) (model/networks.py:104-105): seed w.r.t. z
+    acc[0] += pi; acc[1] += pi * pi; acc[2] += w * (t - pi) * (t - pi);
+    acc[3] += w; acc[4] += w * t; acc[5] += w * t * t; acc[7] += 1.f;
+    fbar[i] = fb;
+    fsum[0] += fb;
+    amax = fmaxf(amax, fabsf(fb));
+  }
+  block_absmax(amax, absmax);
+  block_accumulate<8>(acc, sums, part, 9, 0);
+  __syncthreads();
+  block_accumulate<1>(fsum, fbar_sum, part, 9, 8);
+}
+
 __global__ void sum_kernel(const float* __restrict__ v, long n, double* __restrict__ out, double* __restrict__ part) {
   float acc[1] = {0.f};
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) acc[0] += v[i];
@@ -241,6 +288,23 @@ cudaError_t launch_igr_seeds(const float* f, const float* g, const float* y, int
 }
 cudaError_t launch_label_stats(const float* y, int64_t n, float delta, double* out2, cudaStream_t stream) {
   label_stats_kernel<<<seed_blocks(n), 256, 0, stream>>>(y, n, delta, out2);
+  return cudaGetLastError();
+}
+cudaError_t launch_wsl2_label_stats(const float* y, int64_t n, float delta, float wf, double* out4, cudaStream_t stream) {
+  wsl2_label_stats_kernel<<<seed_blocks(n), 256, 0, stream>>>(y, n, delta, wf, out4);
+  return cudaGetLastError();
+}
+cudaError_t launch_wsl2_seeds(const float* f, const float* y, int64_t n, float delta, float wf, int data_term, const double* stats,
+                              int relu_tanh, unsigned* absmax, float* fbar, double* sums, double* fbar_sum, double* part,
+                              cudaStream_t stream) {
+  const int nb = seed_blocks(n);
+  wsl2_seeds_kernel<<<nb, 256, 0, stream>>>(f, y, n, delta, wf, data_term, stats, relu_tanh, absmax, fbar, sums, fbar_sum, part);
+  if (part) {
+    PartDst d{};
+    for (int i = 0; i < 8; ++i) d.p[i] = sums + i;
+    d.p[8] = fbar_sum;
+    finalize_partials_kernel2<<<1, 32, 0, stream>>>(part, nb, 9, d);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_pcd_seeds(const float* f, const float* g, int64_t n, int which, float coef, int relu_tanh,
@@ -531,7 +595,8 @@ cudaError_t launch_pack_all(const PackAll& pa, cudaStream_t stream) {
 
 
 // Loss value from the (hi, lo) tail of the gradient buffer (after the cross-rank sum): out4 = {total, term0, term1, term2}.
-// kind 0: IGRLOSS (model/losses.py:118-136), kind 1: point-cloud loss (executor/executordistributed.py:73-79).
+// kind 0: IGRLOSS (model/losses.py:118-136), kind 1: point-cloud loss (executor/executordistributed.py:73-79),
+// kind 2: WeightedSmoothL2Loss (model/losses.py:50-69).
 __global__ void loss_value_kernel(const float* __restrict__ tail, int kind, float tau, float lambda_g, int data_term, double inv_n,
                                   double inv_m, float* __restrict__ out4) {
   double s[8];
@@ -542,6 +607,12 @@ __global__ void loss_value_kernel(const float* __restrict__ tail, int kind, floa
     const double reg = s[5] * inv_n, eik = s[6] * inv_n;
     out4[0] = static_cast<float>(data + tau * reg + lambda_g * eik);
     out4[1] = static_cast<float>(data); out4[2] = static_cast<float>(reg); out4[3] = static_cast<float>(eik);
+  } else if (kind == 2) {
+    // WeightedSmoothL2Loss (model/losses.py:50-69): sums = {sum p, sum p^2, sum w (t-p)^2, sum w, sum w t, sum w t^2, -, N}
+    if (inv_n <= 0.0) inv_n = s[7] > 0.0 ? 1.0 / s[7] : 0.0;
+    const double v = data_term == 0 ? s[5] * inv_n - 2.0 * (s[0] * inv_n) * (s[4] * inv_n) + (s[1] * inv_n) * (s[3] * inv_n) : s[2] * inv_n;
+    out4[0] = static_cast<float>(v);
+    out4[1] = static_cast<float>(v); out4[2] = 0.f; out4[3] = 0.f;
   } else {
     const double surf = s[0] * inv_n, eik = s[1] * inv_m;
     out4[0] = static_cast<float>(surf + lambda_g * eik);

@@ -88,6 +88,7 @@ class Engine:
         # hand-over of a finished backward to FusedAdam (optim.py)
         self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._stats4 = torch.zeros(4, dtype=torch.float64, device=self.device)
         self._gbuf = None
         self.acc_ready = False
         self.pending_scale = None
@@ -264,6 +265,20 @@ class Engine:
         self.launches += 1
         return self._stats
 
+    def wsl2_label_stats(self, y, delta, weight_factor):
+        """device double[4] = {sum w, sum w t, sum w t^2, rows} of this shard's labels (model/losses.py:50-69; persistent buffer)."""
+        if self.deterministic:
+            t = y[:, 0].clamp(-delta, delta).double()
+            w = 1.0 + weight_factor * torch.exp(-t.abs())
+            self._stats4[0], self._stats4[1], self._stats4[2] = w.sum(), (w * t).sum(), (w * t * t).sum()
+            self._stats4[3] = float(y.shape[0])
+            return self._stats4
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdfnet_wsl2_label_stats(_ptr(y), int(y.shape[0]), float(delta), float(weight_factor), _ptr(self._stats4),
+                                                        _stream(self.device)), "sdfnet_wsl2_label_stats")
+        self.launches += 1
+        return self._stats4
+
     def loss_value(self, kind, tau=0.0, lambda_g=0.0, data_term=0, n_global=0, m_global=0):
         """float32[4] = {total, term0, term1, term2} from the (all-reduced) tail of the gradient buffer."""
         out = torch.empty(4, dtype=torch.float32, device=self.device)
@@ -352,6 +367,26 @@ class Engine:
                 "sdfnet_train_step_pcd",
             )
         self.launches += 5 * (self._chunks(max(n, 1), 1) + self._chunks(max(m, 1), 1))
+
+
+    def train_step_wsl2(self, x, y, delta, weight_factor, data_term, stats, loss_sums):
+        """One fused WeightedSmoothL2Loss step (include/sdfnet.h sdfnet_train_step_wsl2); stats = the all-reduced
+        wsl2_label_stats of the whole batch."""
+        x = _check_points(x, 3, "x_batch")
+        y = _check_points(y, 4, "y_batch")
+        if y.shape[0] != x.shape[0]:
+            raise ValueError("x_batch and y_batch must have the same number of rows")
+        n = x.shape[0]
+        ws = self.workspace(max(n, 1), 1)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.sdfnet_train_step_wsl2(
+                    self.handle, _ptr(x), _ptr(y), n, float(delta), float(weight_factor), int(data_term), _ptr(stats), _ptr(loss_sums),
+                    _ptr(ws), ws.numel(), _stream(self.device),
+                ),
+                "sdfnet_train_step_wsl2",
+            )
+        self.launches += 5 * self._chunks(max(n, 1), 1)
 
 
 def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):

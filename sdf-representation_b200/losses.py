@@ -133,23 +133,46 @@ class IGRLOSS(nn.Module):
 
 
 class WeightedSmoothL2Loss(nn.Module):
-    """reference model/losses.py:50-69 (the loss the shipped ini selects).  First order only: network forward and
-    backward run in the CUDA library, the [N]-vector loss arithmetic is closed-form moments of the reference's
-    [N,N] broadcast (pairwise) or the per-point form."""
+    """reference model/losses.py:50-69 (the loss the shipped ini selects).  First order only.  Fused like IGRLOSS: one
+    forward that spills the activations, the seeds + loss sums (closed-form moments of the reference's [N,N] broadcast --
+    "pairwise" -- or the per-point form), the adjoint sweep and the first term of the weight-gradient GEMMs (3F per point;
+    the generic autograd route through ``model(x)`` runs the forward twice and pays ~30 small torch kernels per step).
+    ``fused=False`` keeps that generic route (it also serves any model the fused engine does not)."""
 
-    def __init__(self, weight_factor=0.5, delta=0.1, data_term="pairwise"):
+    def __init__(self, weight_factor=0.5, delta=0.1, data_term="pairwise", fused=True):
         super().__init__()
         self.weight_factor = weight_factor
         self.delta = delta
         if data_term not in ("pairwise", "pointwise"):
             raise ValueError("data_term must be 'pairwise' (reference-exact) or 'pointwise'")
         self.data_term = data_term
+        self.fused = bool(fused)
 
     def __name__(self):
         return "WeightedSmoothL2Loss"
 
     def forward(self, x_batch, y_batch, model, epoch):
-        _unwrap(model)
+        net = _unwrap(model)
+        if not self.fused or not torch.is_grad_enabled():
+            return self._generic(x_batch, y_batch, model)
+        eng = net._engine_for(x_batch)
+        world = _dist.world_size()
+        y_batch = y_batch.detach()
+        if y_batch.dtype != torch.float32 or not y_batch.is_contiguous():
+            y_batch = y_batch.float().contiguous()
+        dt = 0 if self.data_term == "pairwise" else 1
+        stats = eng.wsl2_label_stats(y_batch, self.delta, self.weight_factor)
+        if world > 1:
+            _dist.all_reduce_sum(stats)
+        eng.zero_grads()
+        eng._sums.zero_()
+        eng.train_step_wsl2(x_batch, y_batch, self.delta, self.weight_factor, dt, stats, eng._sums)
+        if world > 1:
+            _dist.all_reduce_sum(eng.grad_buffer())
+        out = eng.loss_value(2, data_term=dt)
+        return _FusedLoss.apply(out[0], net, eng, *net._ordered_params())
+
+    def _generic(self, x_batch, y_batch, model):
         t = torch.clamp(y_batch[:, 0], -self.delta, self.delta)
         p = torch.clamp(model(x_batch), -self.delta, self.delta)[:, 0]
         w = 1.0 + self.weight_factor * torch.exp(-torch.abs(t))

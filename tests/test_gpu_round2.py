@@ -564,3 +564,42 @@ def test_training_step_repeats_are_bit_identical_under_stress():
         f1, g1 = net.sdf_and_gradient(x)
         bad += (f1 != f0).sum() + (g1 != g0).sum()
     assert int(bad) == 0
+
+
+@pytest.mark.parametrize("data_term", ["pairwise", "pointwise"])
+@pytest.mark.parametrize("name", ["softplus_skip_128x4.npz", "relu_tanh_128x3.npz"])
+def test_fused_wsl2_equals_generic_autograd_route(name, data_term):
+    """WeightedSmoothL2Loss (model/losses.py:50-69) as one fused first-order step against the same loss written with torch ops
+    on ``model(x)`` (the reference's route through autograd, which the reference goldens pin in test_wsl2_matches_reference):
+    both data terms, softplus + skip and ReLU + tanh nets, a batch with |f| > delta rows (clamp mask), plus FusedAdam."""
+    import sdf_representation_b200 as pkg
+    from test_gpu_parity import make_net
+
+    d = load_golden(name)
+    x = torch.from_numpy(d["x"]).to(dev())
+    y = torch.from_numpy(d["y"]).to(dev())
+    x = torch.cat([x, x * 1.7], 0).contiguous()  # some points far from the surface: |f| > delta, clamped rows
+    y = torch.cat([y, y * 3.0], 0).contiguous()
+    outs = []
+    for fused in (True, False):
+        net = make_net(d, "parity")
+        loss = pkg.WeightedSmoothL2Loss(0.5, 0.1, data_term=data_term, fused=fused)(x, y, net, 0)
+        loss.backward()
+        outs.append((float(loss), [p.grad.detach().cpu().clone() for p in net.parameters()]))
+    assert abs(outs[0][0] - outs[1][0]) < 2e-6 * max(1.0, abs(outs[1][0]))
+    for g0, g1 in zip(outs[0][1], outs[1][1]):
+        if float(g1.norm()) < 1e-12:
+            assert float(g0.norm()) < 1e-7
+        else:
+            assert rel_err(g0, g1) < 2e-4
+    # the fused optimizer tail picks the accumulators of the fused WSL2 step up like those of IGRLOSS
+    net = make_net(d, "parity")
+    opt = pkg.FusedAdam(net, lr=1e-3)
+    w0 = net.lin1.weight.detach().clone()
+    opt.zero_grad()
+    pkg.WeightedSmoothL2Loss(0.5, 0.1, data_term=data_term)(x, y, net, 0).backward()
+    opt.step()
+    dw = (net.lin1.weight.detach() - w0).cpu()
+    ref = outs[1][1][2]  # lin1.weight gradient of the generic route
+    big = ref.abs() > 0.2 * ref.abs().max()
+    assert torch.allclose(dw[big], -1e-3 * torch.sign(ref[big]), atol=2e-5)

@@ -102,13 +102,15 @@ def main():
         from sdf_representation_b200 import inference
 
         dev = torch.device("cuda", 0)
-        for mode in ("fast", "parity"):
+        for mode, optname in (("fast", "FusedAdam"), ("fast", "torch.optim.Adam"), ("parity", "FusedAdam")):
             torch.manual_seed(0)
             net = pkg.ImplicitNet(3, [512] * 8, (), 0, False, precision=mode).to(dev)
-            opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+            opt = pkg.FusedAdam(net, lr=5e-4) if optname == "FusedAdam" else torch.optim.Adam(net.parameters(), lr=5e-4)
             xd, yd = x.to(dev), y.to(dev)
             pipeline(net, pkg.WeightedSmoothL2Loss(0.5, 0.1), opt, xd, yd, dev, lambda: inference.reconstruct_grid(net, GRID))
-            res[f"dropin_{mode}"] = pipeline(net, pkg.WeightedSmoothL2Loss(0.5, 0.1), opt, xd, yd, dev, lambda: inference.reconstruct_grid(net, GRID))
+            key = f"dropin_{mode}" + ("" if optname == "FusedAdam" else "_torch_adam")
+            res[key] = pipeline(net, pkg.WeightedSmoothL2Loss(0.5, 0.1), opt, xd, yd, dev, lambda: inference.reconstruct_grid(net, GRID))
+            res[key]["optimizer"] = optname
     print(json.dumps(res, indent=1))
 
 

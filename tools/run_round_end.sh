@@ -16,6 +16,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 tail -1 gpurun_out/ncu_list.log
 if [ -n "$GRIDPROF" ]; then
   python tools/grid_probe.py 512 > gpurun_out/grid_plain.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"chain_kernel" -s 2 -c 1 -o gpurun_out/prof_grid_$TAG python tools/grid_probe.py 512 > gpurun_out/ncu_grid.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"chain_kernel" -s 1 -c 1 -o gpurun_out/prof_grid_$TAG python tools/grid_probe.py 512 > gpurun_out/ncu_grid.log 2>&1
   tail -1 gpurun_out/ncu_grid.log
 fi
