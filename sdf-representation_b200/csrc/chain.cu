@@ -244,7 +244,8 @@ __device__ __forceinline__ void put_block(const Epi& e, int g, const uint4& v, b
 // ------------------------------------------------------------------------------------------------
 struct Bars {
   uint64_t* acc_full;  // [2]  MMA issuer -> epilogue: accumulator half g is complete
-  uint64_t* a_q;       // [4]  epilogue -> MMA issuer: A-image columns [128 j, 128 j + 128) are in place
+  uint64_t* a_q;       // [5]  epilogue -> MMA issuer: A-image columns [128 j, 128 j + 128) are in place (j < 4); [4]: the
+                       //      EVEN 16-column slices of quarter 3 are in place (SDF_SPLIT_Q3)
   bool remote;         //      CTA pair, rank 1: a relay warp forwards the quarter barriers to the leader CTA
   uint64_t* a_drain;   //      spill-store thread -> epilogue: the bulk stores of the last spilled A image have read it
   uint64_t* a_free;    // [2]  MMA issuer -> epilogue: the MMAs of accumulator half 1 have read A-image quarter j (j = 0, 1)
@@ -262,6 +263,18 @@ struct Bars {
 #endif
 #ifndef SDF_DIRECT_A_TA
 #define SDF_DIRECT_A_TA 0
+#endif
+// SDF_SPLIT_Q3 = 1 (CTA-pair issuer, hot shape): what bounds a layer step is epilogue(half 1) -> the MMAs on the LAST K
+// quarter of the next layer -> epilogue(half 0).  Every epilogue thread writes quarter 3 as two 16-column pieces, and the
+// first pieces of all threads together are exactly the even K = 16 slices of the quarter: they are announced on a_q[4]
+// one piece early, the issuer runs those four MMAs of the last weight chunk at once and only the four odd slices wait for
+// a_q[3] -- the MMA tail after the last epilogue arrival is K = 64 instead of K = 128 (~0.5 k of ~1.3 k cycles per step).
+// Measured (same-session A/B, 1M-point step): tangent + adjoint 13.1 -> 12.6 ms; forward + reverse 8.86 -> 9.03 ms (there the
+// earlier start of the half-0 epilogue runs into its a_free waits), grid inference equal -- so it is on for the tangent /
+// adjoint family only (SDF_SPLIT_Q3 = 2: every family).  The K order of the last chunk changes (even slices, then odd), so
+// results differ from the unsplit order by fp32 summation order, i.e. by fp16 rounding flips downstream.
+#ifndef SDF_SPLIT_Q3
+#define SDF_SPLIT_Q3 1
 #endif
 // Spill images by TMA (SDF_BULK_SPILL = 1).  What the forward / reverse / tangent / adjoint epilogues spill for the
 // weight-gradient GEMM (a_l, q_l, adot_l, Zbar_l) is byte for byte the A operand image they have just written to shared
@@ -303,7 +316,7 @@ __device__ __forceinline__ void arrive_all_quarters(const Bars& B) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 5; ++j) {
       mbar_arrive(&B.a_q[j]);
     }
   }
@@ -951,6 +964,11 @@ __device__ __forceinline__ void hidden_step_staged_v1(Epi& e, const StepIO& io, 
           fence_proxy_async_smem();
           if (st.signal) arrive_quarter(B, 2);
         }
+        if (half == 1 && pc == 2) {
+          // ... and the even 16-column slices of A columns [384,512)
+          fence_proxy_async_smem();
+          if (st.signal) arrive_quarter(B, 4);
+        }
       }
     }
   }
@@ -1123,6 +1141,11 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
           fence_proxy_async_smem();
           if (st.signal) arrive_quarter(B, 2);
         }
+        if (half == 1 && pc == 2) {
+          // ... and the even 16-column slices of A columns [384,512)
+          fence_proxy_async_smem();
+          if (st.signal) arrive_quarter(B, 4);
+        }
       }
     }
   }
@@ -1227,11 +1250,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   uint64_t* peer_full = bars + 2 * NST;   // [NST] pair, leader only: the peer's half chunk has landed
   Bars B;
   B.acc_full = bars + 3 * NST;            // [2]
-  B.a_q = bars + 3 * NST + 2;             // [4]  this CTA's epilogue warps
-  uint64_t* a_qr = bars + 3 * NST + 6;    // [4]  pair, leader only: the peer CTA's quarter is in place (one relayed arrival)
-  B.a_drain = bars + 3 * NST + 10;        //      bulk spill stores of the A image have read it (one arrival by the store thread)
-  B.a_free = bars + 3 * NST + 11;         // [2]  accumulator half 1's MMAs have read A-image quarter 0 / 1 (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 13);
+  B.a_q = bars + 3 * NST + 2;             // [5]  this CTA's epilogue warps
+  uint64_t* a_qr = bars + 3 * NST + 7;    // [5]  pair, leader only: the peer CTA's quarter is in place (one relayed arrival)
+  B.a_drain = bars + 3 * NST + 12;        //      bulk spill stores of the A image have read it (one arrival by the store thread)
+  B.a_free = bars + 3 * NST + 13;         // [2]  accumulator half 1's MMAs have read A-image quarter 0 / 1 (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NST + 15);
   float* gskip = reinterpret_cast<float*>(smem + Cfg::kGskipOff);
 
   const int warp = threadIdx.x >> 5;
@@ -1239,6 +1262,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // this instantiation can contain steps that spill by bulk store (see step_spills_by_bulk)
   constexpr bool kBulkK = SDF_BULK_SPILL && !PAR && ((SW & 1) != 0 || SDF_BULK_SPILL_TA);
+  constexpr bool kSplitQ3 = SDF_SPLIT_Q3 == 2 || (SDF_SPLIT_Q3 == 1 && SW == 2);
 #ifdef SDF_CLOCKS
   // effective SM clock of this launch: SM cycles and global-timer nanoseconds between the start and the end of CTA 0
   long long kclk0 = 0;
@@ -1271,7 +1295,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     mbar_init(B.a_drain, 1);
     mbar_init(&B.a_free[0], 1);
     mbar_init(&B.a_free[1], 1);
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 5; ++j) {
       mbar_init(&B.a_q[j], kEpiWarps);
       mbar_init(&a_qr[j], 1);
     }
@@ -1474,7 +1498,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         for (int it = it0; it < it_end; it += it_step) {
           for (int s = 0; s < p.n_steps; ++s) {
             if (p.steps[s].n_groups == 0) continue;
-            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int jj = 0; jj < 5; ++jj) {
+              const int j = jj < 3 ? jj : (jj == 3 ? 4 : 3);  // completion order: quarters 0, 1, 2, even slices of 3, quarter 3
               mbar_wait(&B.a_q[j], n0 & 1);
               tc_fence_after();
               tc_fence_before();
@@ -1575,8 +1601,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                       tc_fence_after();
                     }
                   } else {  // one weight chunk per 128-column quarter of the A images
-                    mbar_wait_vote_u32(aq_u + 8 * kc, par, poller);
-                    mbar_wait_cluster_vote_u32(aqr_u + 8 * kc, par, poller);
+                    const int jq = (kSplitQ3 && kc == 3) ? 4 : kc;  // last quarter: its even 16-column slices first
+                    mbar_wait_vote_u32(aq_u + 8 * jq, par, poller);
+                    mbar_wait_cluster_vote_u32(aqr_u + 8 * jq, par, poller);
                     tc_fence_after();
                   }
                 }
@@ -1585,6 +1612,34 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                 tc_fence_after();
                 const uint64_t da0 = da_hi | (sA_d + kc * ((8 * 2 * kGranuleBytes) >> 4));
                 const uint64_t db0 = db_hi | (sW_d + stage * (kStage >> 4));
+                if (kSplitQ3 && g == 0 && kc == 3 && k_lo != 0) {
+                  // even K = 16 slices now, odd slices when the whole quarter has arrived
+                  if (elect_one()) {
+#ifdef SDF_CLOCKS
+                    if (!(p.flags & FL_DBG_NO_MMA))
+#endif
+#pragma unroll
+                    for (int k = 0; k < 8; k += 2)
+                      umma_f16_ss2(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc, 1u);
+                  }
+                  __syncwarp();
+                  mbar_wait_vote_u32(aq_u + 8 * 3, par, poller);
+                  mbar_wait_cluster_vote_u32(aqr_u + 8 * 3, par, poller);
+                  tc_fence_after();
+                  if (elect_one()) {
+#ifdef SDF_CLOCKS
+                    if (!(p.flags & FL_DBG_NO_MMA))
+#endif
+#pragma unroll
+                    for (int k = 1; k < 8; k += 2)
+                      umma_f16_ss2(tmem_d, da0 + static_cast<uint64_t>(k) * (2 * kGranuleBytes >> 4), db0 + static_cast<uint64_t>(k) * db_step, idesc, 1u);
+                    umma_commit2_u32(wempty_u + 8 * stage, 3);
+                    umma_commit2_u32(accfull_u + 8 * g, 3);
+                  }
+                  __syncwarp();
+                  if (++stage == NST) { stage = 0; wpar ^= 1; }
+                  continue;
+                }
                 if (elect_one()) {
 #ifdef SDF_CLOCKS
                   if (!(p.flags & FL_DBG_NO_MMA))
