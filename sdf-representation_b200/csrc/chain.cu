@@ -203,6 +203,24 @@ __device__ __forceinline__ void load_acc32(const Epi& e, int c0, float (&v)[32])
   }
 }
 
+// Parity mode, both lane halves working: of the 32 accumulator columns at c0, the threads of lanes 0-63 (e.math) end up
+// with the summed columns c0 .. c0+15 of their point and the threads of lanes 64-127 with c0+16 .. c0+31 -- each half
+// hands the other the 16 columns it does not process through shared memory.  (Round-1 form: lanes 64-127 only ferried
+// their accumulators and half of the epilogue warps did no arithmetic; the parity epilogue is 3 x its MMA time.)
+__device__ __forceinline__ void load_acc16_split(const Epi& e, int c0, float (&v)[16]) {
+  uint32_t r[32];
+  tmem_ld32(e.taddr + c0, r);
+  tmem_ld_wait();
+  const int give = e.math ? 16 : 0;   // first column handed over
+  const int keep = e.math ? 0 : 16;   // first column processed here
+#pragma unroll
+  for (int j = 0; j < 16; ++j) e.scr[(give + j) * kParityPoints + e.prow] = __uint_as_float(e.math ? r[16 + j] : r[j]);
+  named_bar_sync(2 + e.h, 128);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(e.math ? r[j] : r[16 + j]) + e.scr[(keep + j) * kParityPoints + e.prow];
+  named_bar_sync(2 + e.h, 128);
+}
+
 __device__ __forceinline__ uint8_t* img_ptr(uint8_t* base, int layer, int n_tiles, size_t tile, uint32_t ib) {
   return base + (static_cast<size_t>(layer) * n_tiles + tile) * ib;
 }
@@ -736,6 +754,9 @@ __device__ __forceinline__ uint4 granule_fast(const float (&v)[8], const uint4& 
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+#ifndef SDF_PARITY_SPLIT
+#define SDF_PARITY_SPLIT 1
+#endif
 // Hidden-layer epilogue, general form: wait for the whole accumulator, then walk the columns.  Used in parity mode
 // and whenever the GEMM has a single column group (H <= 256).
 template <int DT, bool PAR, int EPI>
@@ -746,6 +767,23 @@ __device__ __forceinline__ void hidden_step_plain(Epi& e, const StepIO& io, cons
   tc_fence_after();
   drain_wait(B, io.drain);
   for (int c0 = e.h * 32; c0 < k.H; c0 += 128) {
+    if constexpr (PAR && SDF_PARITY_SPLIT) {
+      float v16[16];
+      load_acc16_split(e, c0, v16);
+      const int cs = c0 + (e.math ? 0 : 16);
+      Piece<PAR> xa, xb;
+      load_aux<PAR, EPI>(e, io, cs, xa, xb);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float w[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[t] = v16[8 * j + t];
+        const int c = cs + 8 * j;
+        granule_math<DT, PAR, EPI>(e, io, k, c, j, w, xa, xb, gskip);
+        put_granule8<DT, PAR>(e, io.out, c, w);
+      }
+      continue;
+    }
     float v[32];
     load_acc32<PAR>(e, c0, v);
     if (e.math) {
@@ -1769,7 +1807,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       drain = -1;
       const bool fwd_program = SW == 1 || (SW == 3 && first == EPI_FWD_HIDDEN);
       if (fwd_program) {
-        if (e.math) {
+        {
           if (e.valid) {
             if (p.src == SRC_POINTS) {
               e.x[0] = __ldg(p.x + e.grow * 3 + 0);
@@ -1799,7 +1837,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
               for (int j = 0; j < 3; ++j) e.x[j] = -1.f + (2.f * static_cast<float>(ci[j]) + 1.f) * hs;
             }
           }
-          if (e.h < 2) {
+          if (e.math && e.h < 2) {
             const uint4 gx = xblock_granule<DT>(e.x, e.h, 1.f);
             put_block<PAR>(e, e.h, gx, true,
                            (p.flags & FL_SPILL_X) ? p.Ximg + tile * static_cast<size_t>(2 * kGranuleBytes) : nullptr);
@@ -1807,7 +1845,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         }
       } else {
         // tangent / adjoint program: seeds
-        if (e.math) {
+        {
           if (e.valid) {
             e.fb = p.fbar ? __ldg(p.fbar + e.grow) * mult : 0.f;
             if (p.gbar) {
@@ -1818,7 +1856,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           } else {
             e.fb = 0.f;
           }
-          if (e.h < 2) {
+          if (e.math && e.h < 2) {
             const uint4 gg = xblock_granule<DT>(e.x, e.h, 0.f);
             put_block<PAR>(e, e.h, gg, true, p.Gimg + tile * static_cast<size_t>(2 * kGranuleBytes));
             // f-bar block: cols 0-2 = fbar hi/lo/lolo, col 15 = 1
@@ -2139,10 +2177,14 @@ static cudaError_t launch_one(const ChainParams& p, int num_sms, cudaStream_t st
 
 cudaError_t launch_chain(const ChainParams& p, int dtype, int parity, int pair, int num_sms, cudaStream_t stream) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  if (parity) return dtype == DT_BF16 ? launch_one<DT_BF16, true, false>(p, num_sms, stream) : launch_one<DT_FP16, true, false>(p, num_sms, stream);
   // program family of this launch (api.cu builds forward [+ reverse] programs or tangent / adjoint programs)
   bool fr = false, ta = false;
   for (int s = 0; s < p.n_steps; ++s) ((p.steps[s].epi <= EPI_REV_LAST || p.steps[s].epi == EPI_FWD_FUSED) ? fr : ta) = true;
+  if (parity) {
+    if (fr && !ta) return dtype == DT_BF16 ? launch_one<DT_BF16, true, false, 1>(p, num_sms, stream) : launch_one<DT_FP16, true, false, 1>(p, num_sms, stream);
+    if (ta && !fr) return dtype == DT_BF16 ? launch_one<DT_BF16, true, false, 2>(p, num_sms, stream) : launch_one<DT_FP16, true, false, 2>(p, num_sms, stream);
+    return dtype == DT_BF16 ? launch_one<DT_BF16, true, false>(p, num_sms, stream) : launch_one<DT_FP16, true, false>(p, num_sms, stream);
+  }
   if (pair) {
     if (fr && !ta) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true, 1>(p, num_sms, stream) : launch_one<DT_FP16, false, true, 1>(p, num_sms, stream);
     if (ta && !fr) return dtype == DT_BF16 ? launch_one<DT_BF16, false, true, 2>(p, num_sms, stream) : launch_one<DT_FP16, false, true, 2>(p, num_sms, stream);
