@@ -1216,6 +1216,98 @@ __device__ __forceinline__ void hidden_step_staged(Epi& e, const StepIO& io, con
 #endif
 }
 
+// Parity mode at width 512, overlapped form (SDF_PARITY_STAGED): as in the fast mode the epilogue of accumulator half 0 runs
+// while the MMAs of half 1 still read the A image -- its packed hi / lo results are parked in the TMEM columns it has
+// consumed and move to shared memory when half 1 has completed -- and the quarters of the A image are released as they are
+// written, so the next layer's hi-pass MMAs start under the half-1 epilogue.  Each thread owns 16 of the 32 columns of a
+// chunk (load_acc16_split); arithmetic is the general fp32 form (granule_math).
+#ifndef SDF_PARITY_STAGED
+#define SDF_PARITY_STAGED 1
+#endif
+template <int DT, int EPI>
+__device__ __forceinline__ void hidden_step_staged_par(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
+                                                       uint32_t par0, uint32_t par1, float* gskip) {
+  const int sub = e.math ? 0 : 16;  // this thread's 16 columns inside every 32-column chunk
+  const int lo_row = e.prow + kParityPoints;
+  mbar_wait(&B.acc_full[0], par0);
+  tc_fence_after();
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    if (half == 1) {
+      tmem_st_wait();
+      mbar_wait(&B.acc_full[1], par1);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = ci * 128 + e.h * 32;
+        uint32_t r[16];
+        tmem_ld16(e.taddr + c0, r);
+        tmem_ld_wait();
+        st_smem_v4(e.sA + img_off(c0 + sub, e.prow), make_uint4(r[0], r[1], r[2], r[3]));
+        st_smem_v4(e.sA + img_off(c0 + sub + 8, e.prow), make_uint4(r[4], r[5], r[6], r[7]));
+        st_smem_v4(e.sA + img_off(c0 + sub, lo_row), make_uint4(r[8], r[9], r[10], r[11]));
+        st_smem_v4(e.sA + img_off(c0 + sub + 8, lo_row), make_uint4(r[12], r[13], r[14], r[15]));
+      }
+      fence_proxy_async_smem();
+      if (st.signal) {
+        tc_fence_before();
+        arrive_quarter(B, 0);
+        arrive_quarter(B, 1);
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const int c0 = half * 256 + ci * 128 + e.h * 32;
+      float v16[16];
+      load_acc16_split(e, c0, v16);
+      const int cs = c0 + sub;
+      Piece<true> xa, xb;
+      load_aux<true, EPI>(e, io, cs, xa, xb);
+      uint4 ph[2], pl[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float w[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[t] = v16[8 * j + t];
+        const int c = cs + 8 * j;
+        granule_math<DT, true, EPI>(e, io, k, c, j, w, xa, xb, gskip);
+        float hi[8], lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          hi[t] = H16<DT>::rnd(w[t]);
+          lo[t] = w[t] - hi[t];
+        }
+        ph[j] = pack8<DT>(hi);
+        pl[j] = pack8<DT>(lo);
+        if (io.out) {
+          *reinterpret_cast<uint4*>(io.out + img_off(c, e.prow)) = ph[j];
+          *reinterpret_cast<uint4*>(io.out + img_off(c, lo_row)) = pl[j];
+        }
+      }
+      if (half == 0) {
+        const uint32_t pk[16] = {ph[0].x, ph[0].y, ph[0].z, ph[0].w, ph[1].x, ph[1].y, ph[1].z, ph[1].w,
+                                 pl[0].x, pl[0].y, pl[0].z, pl[0].w, pl[1].x, pl[1].y, pl[1].z, pl[1].w};
+        tmem_st16(e.taddr + c0, pk);  // park in the first 16 of the 32 accumulator columns this thread has consumed
+      } else {
+        st_smem_v4(e.sA + img_off(cs, e.prow), ph[0]);
+        st_smem_v4(e.sA + img_off(cs + 8, e.prow), ph[1]);
+        st_smem_v4(e.sA + img_off(cs, lo_row), pl[0]);
+        st_smem_v4(e.sA + img_off(cs + 8, lo_row), pl[1]);
+        if (ci == 0) {
+          fence_proxy_async_smem();
+          if (st.signal) arrive_quarter(B, 2);
+        }
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  if (st.signal) {
+    tc_fence_before();
+    arrive_quarter(B, 4);
+    arrive_quarter(B, 3);
+  }
+}
+
 template <int DT, bool PAR, int EPI>
 __device__ __forceinline__ void hidden_step(Epi& e, const StepIO& io, const EpiConst& k, const StepDesc& st, const Bars& B,
                                             uint32_t& n0, uint32_t& n1, float* gskip) {
@@ -1227,6 +1319,9 @@ __device__ __forceinline__ void hidden_step(Epi& e, const StepIO& io, const EpiC
       hidden_step_staged_v1<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
     else
       hidden_step_staged<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
+  }
+  else if (PAR && SDF_PARITY_STAGED && SDF_PARITY_SPLIT && st.n_groups == 2 && !k.relu) {
+    if constexpr (PAR) hidden_step_staged_par<DT, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
   }
   else hidden_step_plain<DT, PAR, EPI>(e, io, k, st, B, n0 & 1, n1 & 1, gskip);
   ++n0;
