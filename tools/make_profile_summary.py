@@ -49,7 +49,16 @@ open(f"{P}/{tag}_bench_1xB200.txt", "w").write(out)
 print(out)
 
 rep = f"{G}/prof_step_{tag}.ncu-rep"
-if os.path.exists(rep):
+pre = f"{G}/ncu_step_summary_{tag}.txt"
+if os.path.exists(pre) and os.path.getsize(pre) > 0:
+    # summarised on the GPU box (tools/run_round_end.sh): the report itself may not have come back (64 MiB merge limit)
+    import shutil
+    shutil.copy(pre, f"{P}/{tag}_train_step_1M_ncu.txt")
+    if os.path.exists(f"{G}/dram_bytes_per_point_{tag}.json"):
+        shutil.copy(f"{G}/dram_bytes_per_point_{tag}.json", f"{P}/dram_bytes_per_point.json")
+    if os.path.exists(f"{G}/ncu_grid_summary_{tag}.txt"):
+        shutil.copy(f"{G}/ncu_grid_summary_{tag}.txt", f"{P}/{tag}_grid_512_fwd_kernel_ncu.txt")
+elif os.path.exists(rep):
     txt = subprocess.run([sys.executable, f"{ROOT}/tools/ncu_summary.py", rep, "14", "--json", f"{P}/dram_bytes_per_point.json", "--points", str(b["config"]["points_per_gpu"])], capture_output=True, text=True).stdout
     open(f"{P}/{tag}_train_step_1M_ncu.txt", "w").write(txt)
 

@@ -19,3 +19,11 @@ if [ -n "$GRIDPROF" ]; then
   ncu --set full --clock-control none --import-source on -k regex:"chain_kernel" -s 1 -c 1 -o gpurun_out/prof_grid_$TAG python tools/grid_probe.py 512 > gpurun_out/ncu_grid.log 2>&1
   tail -1 gpurun_out/ncu_grid.log
 fi
+# summaries on the box (ncu -i needs no GPU); the reports themselves come back only while gpurun_out stays under the 64 MiB
+# merge limit
+[ -f gpurun_out/prof_step_$TAG.ncu-rep ] && python tools/ncu_summary.py gpurun_out/prof_step_$TAG.ncu-rep 14 --json gpurun_out/dram_bytes_per_point_$TAG.json --points 1048576 > gpurun_out/ncu_step_summary_$TAG.txt 2>/dev/null
+[ -f gpurun_out/prof_grid_$TAG.ncu-rep ] && python tools/ncu_summary.py gpurun_out/prof_grid_$TAG.ncu-rep 16 > gpurun_out/ncu_grid_summary_$TAG.txt 2>/dev/null
+for f in gpurun_out/prof_grid_$TAG.ncu-rep gpurun_out/prof_step_$TAG.ncu-rep; do
+  if [ "$(du -sm gpurun_out | cut -f1)" -ge 60 ] && [ -f $f ]; then echo "dropping $f (merge limit)"; rm -f $f; fi
+done
+
