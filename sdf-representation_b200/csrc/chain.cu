@@ -15,11 +15,14 @@
 //   fast   : tile = 128 points, one 16-bit operand per value, one MMA pass             (error ~ 2^-11 relative)
 //   parity : tile = 64 points; image rows 0-63 hold hi = rnd16(v), rows 64-127 hold lo = rnd16(v - hi); the weight
 //            stream carries W_hi chunks then W_lo chunks.  One M=128 accumulator then holds v_hi.(W_hi+W_lo) in lanes
-//            0-63 and v_lo.(W_hi+W_lo) in lanes 64-127; the epilogue adds the two lane halves (fp32-grade result).
+//            0-63 and v_lo.(W_hi+W_lo) in lanes 64-127; the epilogue adds the two lane halves (fp32-grade result); each
+//            half does the arithmetic of 16 of every 32 columns (load_acc16_split).
 //
-// Overlap (fast mode, H = 512): the 128 x 512 accumulator is two 256-column halves with their own completion
-// barriers.  The epilogue of half 0 runs while the MMAs of half 1 still read the A image; the epilogue of half 1 runs
-// while the next layer's MMAs already consume the K < 256 part of the new A image (hidden_step_staged).
+// Overlap (H = 512): the 128 x 512 accumulator is two 256-column halves with their own completion barriers.  The
+// epilogue of half 0 runs while the MMAs of half 1 still read the A image -- its results go straight into the quarters
+// those MMAs have left (SDF_DIRECT_A, forward / reverse) or are parked in TMEM until they have finished (tangent /
+// adjoint, parity mode) --; the epilogue of half 1 runs while the next layer's MMAs already consume the K < 256 part
+// of the new A image (hidden_step_staged, hidden_step_staged_v1, hidden_step_staged_par).
 //
 // Warp roles (640 threads = 5 warpgroups; setmaxnreg moves registers from the last warpgroup to the epilogue):
 //   warps 0-15  epilogue: warp w owns TMEM lanes 32*(w%4).. (tile rows) and column quarter w/4 of every 128-column block
@@ -27,7 +30,8 @@
 //   warp 17     MMA issuer: warp-uniform loop, one elected lane issues (pair kernel, peer CTA: "my weight half has
 //               landed" relay)
 //   warp 18     pair kernel, peer CTA: relays the completed A-image quarters to the leader CTA; otherwise idle
-//   warp 19     idle
+//   warp 19     forward / reverse programs: spill-store thread (bulk copies of completed A-image quarters to the spill
+//               images, SDF_BULK_SPILL); otherwise idle
 // Four epilogue warps per SM sub-partition give the latency hiding (TMEM reads, spill-image loads, MUFU) that the
 // accumulator hand-off needs.
 //
