@@ -1,5 +1,6 @@
 """Test infrastructure: a CPU stand-in for ``engine.Engine`` whose arithmetic is the oracle.  It lets the gloo tests run
-the PRODUCT host code of the multi-GPU step (``losses.IGRLOSS.forward`` / ``PointCloudLoss.forward``: label statistics,
+the PRODUCT host code of the multi-GPU step (``losses.IGRLOSS.forward`` / ``PointCloudLoss.forward`` /
+``WeightedSmoothL2Loss.forward``: label statistics,
 the one sum-allreduce of [gradients | loss sums], the loss value, the autograd hand-over) without a GPU.  It mirrors the
 engine methods those functions call and nothing else; it is never importable from the package."""
 import torch
@@ -87,8 +88,39 @@ class FakeEngine:
         sums[1] += ((gn - 1) ** 2).sum()
         self._mirror()
 
+    def wsl2_label_stats(self, y, delta, weight_factor):
+        t = y[:, 0].double().clamp(-delta, delta)
+        w = 1.0 + weight_factor * torch.exp(-t.abs())
+        self._stats4 = torch.stack([w.sum(), (w * t).sum(), (w * t * t).sum(), torch.tensor(float(y.shape[0]), dtype=torch.float64)])
+        return self._stats4
+
+    def train_step_wsl2(self, x, y, delta, weight_factor, data_term, stats, sums):
+        # model/losses.py:50-69 differentiated by hand: fbar = [|f| <= delta] (2/N)(p mean(w) - mean(w t))
+        W, b = self._params()
+        x, y = x.double(), y.double()
+        N = float(stats[3])
+        f = orc.forward(W, b, x, self.skip, self.beta)
+        p = f.clamp(-delta, delta)
+        t = y[:, 0].clamp(-delta, delta)
+        w = 1.0 + weight_factor * torch.exp(-t.abs())
+        inside = ((f >= -delta) & (f <= delta)).double()
+        if data_term == 0:
+            fbar = (2.0 / N) * (p * float(stats[0]) / N - float(stats[1]) / N) * inside
+        else:
+            fbar = (2.0 / N) * w * (p - t) * inside
+        dW, db = orc.param_grads(W, b, x, self.skip, self.beta, fbar, None)
+        self._add_grads(dW, db)
+        sums += torch.stack([p.sum(), (p * p).sum(), (w * (t - p) ** 2).sum(), w.sum(), (w * t).sum(), (w * t * t).sum(),
+                             torch.zeros((), dtype=torch.float64), torch.tensor(float(x.shape[0]), dtype=torch.float64)])
+        self._mirror()
+
     def loss_value(self, kind, tau=0.0, lambda_g=0.0, data_term=0, n_global=0, m_global=0):
         s = self._gbuf[self.num_params: self.num_params + 16:2]
+        if kind == 2:
+            N = float(s[7])
+            v = s[5] / N - 2 * (s[0] / N) * (s[4] / N) + (s[1] / N) * (s[3] / N) if data_term == 0 else s[2] / N
+            z = torch.zeros((), dtype=torch.float64)
+            return torch.stack([v, v, z, z])
         if kind == 0:
             N = float(n_global) if n_global > 0 else float(s[7])
             data = s[1] / N + s[3] / N - 2 * (s[0] / N) * (s[2] / N) if data_term == 0 else s[4] / N

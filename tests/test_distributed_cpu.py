@@ -1,5 +1,5 @@
 """CPU, world_size 2, gloo: the PRODUCT host code of the data-parallel step (losses.IGRLOSS.forward /
-PointCloudLoss.forward: label statistics, one sum-allreduce of [gradients | loss sums], loss value, autograd hand-over;
+PointCloudLoss.forward / WeightedSmoothL2Loss.forward: label statistics, one sum-allreduce of [gradients | loss sums], loss value, autograd hand-over;
 distributed.shard_rows / broadcast_parameters) on UNEQUAL shards gives the single-process result.  The per-rank engine
 is tests/fake_engine.py (oracle arithmetic): the CUDA engine needs a GPU, the host logic around it does not."""
 import os
@@ -33,13 +33,16 @@ def _run_losses(pkg, orc, FakeEngine, x, y, xp, lo, hi, plo, phi, D):
         ("igr_pairwise", pkg.IGRLOSS(0.1, 1.0, 0.1, 1.0), (x[lo:hi], y[lo:hi])),
         ("igr_pointwise_mask", pkg.IGRLOSS(0.1, 1.0, 0.1, 0.05, data_term="pointwise"), (x[lo:hi], y[lo:hi])),
         ("pcd", pkg.PointCloudLoss(0.1), (x[lo:hi], xp[plo:phi])),
+        ("wsl2_pairwise", pkg.WeightedSmoothL2Loss(0.5, 0.1), (x[lo:hi], y[lo:hi])),
+        ("wsl2_pointwise", pkg.WeightedSmoothL2Loss(0.5, 0.1, data_term="pointwise"), (x[lo:hi], y[lo:hi])),
     ):
         for p in net.parameters():
             p.grad = None
         loss = crit(*args, net, 0)
         loss.backward()
+        terms = getattr(crit, "last_terms", None)
         out[name] = (float(loss.detach()), torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone(),
-                     None if crit.last_terms is None else crit.last_terms.clone())
+                     torch.zeros(1, dtype=torch.float64) if terms is None else terms.clone())
     return out
 
 
@@ -85,6 +88,11 @@ def _worker(rank, world, port, ret):
         lref, _, dW, db = orc.igr_loss_and_grads(W, b, x, y, (2,), 100.0, f32(0.1), 1.0, f32(0.1), f32(0.05), "pointwise")
         ref = torch.cat([t.reshape(-1) for pair in zip(dW, db) for t in pair])
         ret["oracle"] = (abs(single["igr_pointwise_mask"][0] - float(lref)), float((single["igr_pointwise_mask"][1] - ref).norm() / ref.norm()))
+        # the fused WeightedSmoothL2Loss host path against the oracle's restatement of model/losses.py:50-69 (both data terms)
+        for key, dt in (("wsl2_pairwise", "pairwise"), ("wsl2_pointwise", "pointwise")):
+            lw, dWw, dbw = orc.wsl2_loss_and_grads(W, b, x, y, (2,), 100.0, 0.5, 0.1, dt)  # (python floats reach the fake engine unrounded)
+            refw = torch.cat([t.reshape(-1) for pair in zip(dWw, dbw) for t in pair])
+            ret["oracle_" + key] = (abs(single[key][0] - float(lw)), float((single[key][1] - refw).norm() / refw.norm()))
 
 
 def test_sharded_step_equals_single_process():
@@ -93,7 +101,9 @@ def test_sharded_step_equals_single_process():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    for name in ("igr_pairwise", "igr_pointwise_mask", "pcd"):
+    for name in ("igr_pairwise", "igr_pointwise_mask", "pcd", "wsl2_pairwise", "wsl2_pointwise"):
         dl, dg, dt = ret[name]
         assert dl < 1e-12 and dg < 1e-10 and dt < 1e-12, (name, dl, dg, dt)
     assert ret["oracle"][0] < 1e-10 and ret["oracle"][1] < 1e-9
+    for key in ("oracle_wsl2_pairwise", "oracle_wsl2_pointwise"):
+        assert ret[key][0] < 1e-10 and ret[key][1] < 1e-9, (key, ret[key])
