@@ -237,6 +237,14 @@ extern "C" int sdfnet_create(const sdfnet_desc* desc, sdfnet_t* out) {
 }
 
 static int init_handle(sdfnet_handle* h, const sdfnet_desc* desc, int num_sms) {
+  {
+    // keep freed blocks of the stream-ordered pool cached (default: released at the next synchronisation)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, desc->device) == cudaSuccess && pool) {
+      uint64_t keep = 64ull << 20;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   h->d = *desc;
   h->H = desc->hidden;
   h->L = desc->num_hidden;
@@ -1181,6 +1189,10 @@ extern "C" int sdfnet_mc_edge_vertices(const float* sdf, int32_t nx, int32_t ny,
   return 0;
 }
 
+// The three handle-free scan entry points below take their block-sum scratch (8 bytes per 1024 elements) from the device's
+// stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the caller's stream): no synchronisation, safe for concurrent
+// streams -- a cached buffer would need a handle or a lock -- and after its first use the pool serves the request from
+// memory it already holds (sdfnet_create raises the pool's release threshold so it keeps it).
 extern "C" int sdfnet_mc_triangles(const uint8_t* case_index, const int64_t* active_cells, int64_t n_active, int64_t* tri_vertex_index,
                                    int64_t* n_tri, void* stream_) {
   if (!case_index || !n_tri || (n_active > 0 && !active_cells)) return fail(1, "sdfnet_mc_triangles: null argument");
